@@ -1,0 +1,23 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def oracle_lib():
+    """Build the oracle's C restatement on demand (test infrastructure only)."""
+    import subprocess
+
+    odir = os.path.join(ROOT, "oracle")
+    if not os.path.exists(os.path.join(odir, "libkod_oracle.so")):
+        subprocess.check_call(["make", "-C", odir])
+    return os.path.join(odir, "libkod_oracle.so")

@@ -1,0 +1,292 @@
+"""Generate the golden fixtures by running the REAL reference (`/root/reference`, imported with the
+stubs of `_ref_harness.py`) on small seeded inputs.  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+Writes tests/golden/{assign,loss,decode,nms}_*.npz.  Each file stores the inputs and the reference's
+outputs, so the GPU box (which has no /root/reference) can check both the oracle and the CUDA path.
+No fixture exists for the mAP stage: its arithmetic lives in pycocotools, which is absent
+("parity unpinned", see oracle/coco_map.py).
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+
+import _ref_harness  # noqa: E402
+
+assert _ref_harness.install(), "reference tree not found"
+
+import torchvision  # noqa: E402
+from kod.core.anchors.info import AnchorBoxInfo  # noqa: E402
+from kod.core.bbox.iou import IoUCalculator, IoUType  # noqa: E402
+from kod.core.label_assignment.yv5 import AssignmentAnchorInfo, Yolov5LabelAssigner  # noqa: E402
+from kod.core.types import FeatureShape  # noqa: E402
+from kod.data.detection import DetectionTarget  # noqa: E402
+from kod.lightning.experiments.yv5_baseline.exp import DefaultYolov5Experiment  # noqa: E402
+from kod.lightning.experiments.yv5_baseline.loss import Yolov5Loss, Yolov5LossParams  # noqa: E402
+from kod.lightning.experiments.yv5_baseline.type_defs import LayerwiseAnchorInfo  # noqa: E402
+from kod.nn.heads.types import DetectionHeadResult  # noqa: E402
+from kod.nn.networks.yolov5 import Yolov5NetworkResult  # noqa: E402
+import kod.core.nms as ref_nms_mod  # noqa: E402
+
+from object_detection_cib_b200 import synthetic as syn  # noqa: E402
+
+LEVEL_NAMES = ("ll", "ml", "hl")
+
+
+def anchor_infos():
+    return [AnchorBoxInfo(stride=s, boxes_wh=[FeatureShape(width=w, height=h) for (w, h) in a])
+            for s, a in zip(syn.STRIDES, syn.ANCHORS_PX)]
+
+
+def ref_targets(targets):
+    return tuple(DetectionTarget(boxes=b, labels=l) for b, l in targets)
+
+
+def pack_targets(targets, prefix="t"):
+    d = {f"{prefix}_n": np.array([t[0].shape[0] for t in targets], np.int64)}
+    boxes = [t[0].reshape(-1, 4) for t in targets]
+    labels = [t[1].reshape(-1) for t in targets]
+    dtype = boxes[0].dtype if boxes else torch.float32
+    d[f"{prefix}_boxes"] = torch.cat(boxes, 0).numpy() if boxes else np.zeros((0, 4), np.float32)
+    d[f"{prefix}_labels"] = torch.cat(labels, 0).numpy().astype(np.int64) if labels else np.zeros((0,), np.int64)
+    return d
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+# ------------------------------------------------------------------------------------------------
+# target assignment
+# ------------------------------------------------------------------------------------------------
+def run_assign(name, targets, img_w, img_h, threshold=4.0):
+    infos = anchor_infos()
+    assigner = Yolov5LabelAssigner(AssignmentAnchorInfo(*infos), threshold=threshold)
+    res = assigner(FeatureShape(width=img_w, height=img_h), ref_targets(targets))
+    out = pack_targets(targets)
+    out["img_wh"] = np.array([img_w, img_h], np.int64)
+    out["threshold"] = np.array([threshold], np.float64)
+    for ln, r in zip(LEVEL_NAMES, res):
+        out[f"{ln}_samples"] = r.indices.samples.numpy()
+        out[f"{ln}_anchors"] = r.indices.anchors.numpy()
+        out[f"{ln}_grid_y"] = r.indices.grid_y.numpy()
+        out[f"{ln}_grid_x"] = r.indices.grid_x.numpy()
+        out[f"{ln}_labels"] = r.labels.numpy()
+        out[f"{ln}_gt_boxes"] = r.gt_boxes.numpy().reshape(-1, 4)
+        out[f"{ln}_anchor_wh"] = r.anchors.numpy().reshape(-1, 2)
+    save(name, **out)
+
+
+def assign_cases():
+    # a1: the SURVEY A.1-7 example (two identical GT in one cell, one GT in a second image)
+    t = [(torch.tensor([[100.0, 100, 160, 170], [100, 100, 160, 170]]), torch.tensor([1, 3])),
+         (torch.tensor([[300.0, 300, 420, 380]]), torch.tensor([0]))]
+    run_assign("assign_kat", t, 640, 640)
+    # a2: random cfg-1 shaped batch with one empty image
+    run_assign("assign_rand640", syn.make_targets(8, 640, 10, seed=2024, empty_images=(3,)), 640, 640)
+    # a3: the reference's default 416 input (52/26/13 grids), fp64 boxes as produced by the numpy pipeline
+    run_assign("assign_rand416_f64", syn.make_targets(5, 416, 10, seed=2025, n_max=20, dtype=torch.float64,
+                                                      size_hi=300.0), 416, 416)
+    # a4: hand-made edge cases: centres on cell boundaries (duplicate rows), centres within one cell of the
+    # border (neighbour masks off), zero-size / huge boxes (filtered by every anchor), non-square image
+    e = [
+        (torch.tensor([[64.0, 64, 96, 96],      # centre (80,80): on the ll/ml boundary grid
+                       [0.0, 0, 14, 14],        # centre (7,7): < 1 cell from the border on every level
+                       [300.0, 200, 300, 200],  # zero size
+                       [0.0, 0, 639, 479],      # huge
+                       [630.0, 470, 639, 479],  # bottom-right corner
+                       [100.5, 100.25, 130.5, 121.75]]), torch.tensor([0, 9, 2, 3, 4, 5])),
+        (torch.zeros(0, 4), torch.zeros(0, dtype=torch.long)),
+        (torch.tensor([[320.0, 240, 352, 272], [320.0, 240, 352, 272], [322.0, 241, 350, 271]]),
+         torch.tensor([7, 7, 1])),
+    ]
+    run_assign("assign_edges", e, 640, 480)
+    # a5: every image empty
+    z = [(torch.zeros(0, 4), torch.zeros(0, dtype=torch.long)) for _ in range(3)]
+    run_assign("assign_empty", z, 640, 640)
+    # a6: a different threshold
+    run_assign("assign_thr2", syn.make_targets(4, 320, 10, seed=2026, n_max=12), 320, 320, threshold=2.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# loss forward + backward
+# ------------------------------------------------------------------------------------------------
+def net_result(heads, requires_grad=False):
+    lv = []
+    for h in heads:
+        ts = [t.detach().clone() for t in h]  # clones of the permuted views keep the planar strides
+        if requires_grad:
+            for t in ts:
+                t.requires_grad_(True)
+        lv.append(DetectionHeadResult(*ts))
+    return Yolov5NetworkResult(*lv)
+
+
+def run_loss(name, B, S, C, targets, weights, iou_type="ciou", seed=11, hp=None):
+    heads = syn.make_head(B, S, C, seed=seed, obj_shift=3.0)
+    infos = anchor_infos()
+    assigner = Yolov5LabelAssigner(AssignmentAnchorInfo(*infos))
+    hp = hp or Yolov5LossParams.get_default()
+    loss_mod = Yolov5Loss(assigner, hp, IoUCalculator(IoUType(iou_type), eps=1e-7), weights=weights)
+    nr = net_result(heads, requires_grad=True)
+    res = loss_mod(FeatureShape(width=S, height=S), nr, ref_targets(targets))
+    total = B * (res.localization + res.classification + res.objectness)  # exp.py:124-130
+    total.backward()
+    out = pack_targets(targets)
+    out["meta"] = np.array([B, S, C], np.int64)
+    out["iou_type"] = np.array([iou_type])
+    out["hparams"] = np.array(list(hp), np.float64)
+    out["weights"] = np.array(weights if weights is not None else [], np.float32)
+    out["losses"] = np.array([res.localization.item(), res.objectness.item(), res.classification.item()],
+                             np.float32)
+    for ln, h, r in zip(LEVEL_NAMES, heads, nr):
+        for part, src, leaf in zip(("box", "obj", "cls"), h, r):
+            # store in the physical planar layout (B, A*P, H, W)
+            out[f"{ln}_{part}"] = src.permute(0, 1, 4, 2, 3).contiguous().numpy().reshape(
+                B, -1, src.shape[2], src.shape[3])
+            g = leaf.grad if leaf.grad is not None else torch.zeros_like(leaf)
+            out[f"{ln}_d{part}"] = g.permute(0, 1, 4, 2, 3).contiguous().numpy().reshape(
+                B, -1, src.shape[2], src.shape[3])
+    save(name, **out)
+
+
+def loss_cases():
+    w10 = syn.readme_class_weights()
+    t = syn.make_targets(3, 96, 10, seed=31, n_min=1, n_max=6, size_lo=4, size_hi=90)
+    # force a duplicate cell: repeat the first GT of image 0 with another label
+    b0, l0 = t[0]
+    t[0] = (torch.cat((b0, b0[:1]), 0), torch.cat((l0, torch.tensor([(int(l0[0]) + 1) % 10])), 0))
+    run_loss("loss_ciou_w", 3, 96, 10, t, w10)
+    run_loss("loss_ciou_now", 2, 128, 4, syn.make_targets(2, 128, 4, seed=32, n_min=2, n_max=5, size_hi=120),
+             None, seed=12)
+    for it in ("iou", "giou", "diou"):
+        run_loss(f"loss_{it}", 2, 64, 3, syn.make_targets(2, 64, 3, seed=33, n_min=2, n_max=4, size_hi=60),
+                 [1.0, 2.0, 3.0], iou_type=it, seed=13)
+    # empty level(s): only one tiny box -> ml/hl unassigned -> NaN loc/cls
+    tiny = [(torch.tensor([[10.0, 10, 22, 24]]), torch.tensor([2])), (torch.zeros(0, 4), torch.zeros(0, dtype=torch.long))]
+    run_loss("loss_empty_levels", 2, 96, 10, tiny, w10, seed=14)
+    # non-multiple-of-4 grids (13x13 / 6x6 / 3x3) and non-default lambdas
+    hp = Yolov5LossParams(0.3, 0.07, 0.9, 3.0, 1.5, 0.5)
+    run_loss("loss_s104", 2, 104, 10, syn.make_targets(2, 104, 10, seed=34, n_min=2, n_max=5, size_hi=100),
+             w10, seed=15, hp=hp)
+
+
+# ------------------------------------------------------------------------------------------------
+# decode
+# ------------------------------------------------------------------------------------------------
+class _Exp:
+    """Only what `get_detections` touches (exp.py:70-102)."""
+
+    def __init__(self):
+        self.anchor_info = LayerwiseAnchorInfo(*anchor_infos())
+
+    get_detections = DefaultYolov5Experiment.get_detections
+
+
+def run_decode(name, B, S, C, seed, obj_shift=0.0):
+    heads = syn.make_head(B, S, C, seed=seed, obj_shift=obj_shift)
+    det = _Exp().get_detections(FeatureShape(width=S, height=S), net_result(heads))
+    out = {"meta": np.array([B, S, C], np.int64), "detections": det.numpy()}
+    for ln, h in zip(LEVEL_NAMES, heads):
+        for part, src in zip(("box", "obj", "cls"), h):
+            out[f"{ln}_{part}"] = src.permute(0, 1, 4, 2, 3).contiguous().numpy().reshape(
+                B, -1, src.shape[2], src.shape[3])
+    save(name, **out)
+    return det
+
+
+def decode_cases():
+    run_decode("decode_s96", 2, 96, 10, seed=41)
+    run_decode("decode_s104", 2, 104, 3, seed=42)  # 13x13 / 6x6 / 3x3 planes
+
+
+# ------------------------------------------------------------------------------------------------
+# NMS
+# ------------------------------------------------------------------------------------------------
+def run_nms(name, det, conf, iou, classes=None):
+    rec = []
+    real = torchvision.ops.nms
+
+    def spy(boxes, scores, thr):
+        keep = real(boxes, scores, thr)
+        rec.append((boxes.clone(), scores.clone(), keep.clone()))
+        return keep
+
+    torchvision.ops.nms = spy
+    try:
+        res = ref_nms_mod.non_max_suppression(det.clone(), conf_thres=conf, nms_thres=iou, classes=classes)
+    finally:
+        torchvision.ops.nms = real
+    out = {"detections": det.numpy(), "conf_iou": np.array([conf, iou], np.float64),
+           "classes": np.array(classes if classes is not None else [], np.int64),
+           "counts": np.array([r.shape[0] for r in res], np.int64)}
+    # the spy is only called for images that reach NMS; map calls back to images by order
+    call = 0
+    for b, r in enumerate(res):
+        out[f"out_{b}"] = r.numpy().reshape(-1, 6)
+        if r.shape[0]:
+            boxes, scores, keep = rec[call]
+            call += 1
+            out[f"keep_{b}"] = keep[:300].numpy()
+            out[f"ncand_{b}"] = np.array([boxes.shape[0]], np.int64)
+        else:
+            out[f"keep_{b}"] = np.zeros((0,), np.int64)
+            # an image can reach NMS and still... no: NMS always keeps >= 1 box when n >= 1
+            out[f"ncand_{b}"] = np.array([0], np.int64)
+    assert call == len(rec)
+    save(name, **out)
+
+
+def synthetic_detections(B, N, C, seed, img=640.0, clusters=40, tie_every=0):
+    """Decoded-detection-like matrix with heavy overlaps: boxes jitter around cluster centres."""
+    g = torch.Generator()
+    g.manual_seed(seed)
+    cen = torch.rand(B, clusters, 2, generator=g) * img
+    size = 20 + torch.rand(B, clusters, 2, generator=g) * 150
+    which = torch.randint(0, clusters, (B, N), generator=g)
+    c = torch.gather(cen, 1, which[..., None].expand(-1, -1, 2)) + torch.randn(B, N, 2, generator=g) * 6
+    s = torch.gather(size, 1, which[..., None].expand(-1, -1, 2)) * (1 + 0.15 * torch.randn(B, N, 2, generator=g)).abs()
+    box = torch.cat((c - s / 2, c + s / 2), -1)
+    obj = torch.rand(B, N, 1, generator=g) ** 2
+    cls = torch.rand(B, N, C, generator=g) ** 3
+    if tie_every:
+        obj[:, ::tie_every] = 0.5
+        cls[:, ::tie_every] = 0.25
+    return torch.cat((box, obj, cls), -1).float()
+
+
+def nms_cases():
+    det = run_decode("decode_s96_dense", 2, 96, 10, seed=43, obj_shift=4.0)
+    run_nms("nms_decoded", det, 0.001, 0.6)
+    run_nms("nms_clustered", synthetic_detections(3, 1200, 10, seed=51, tie_every=7), 0.001, 0.6)
+    run_nms("nms_default_thr", synthetic_detections(2, 800, 10, seed=52), 0.25, 0.45)
+    run_nms("nms_single_class", synthetic_detections(2, 900, 1, seed=53), 0.05, 0.5)
+    run_nms("nms_class_filter", synthetic_detections(2, 500, 6, seed=54), 0.01, 0.6, classes=[1, 4])
+    d = synthetic_detections(2, 400, 5, seed=55)
+    d[1, :, 4] = 0.0  # image 1: nothing above the objectness threshold
+    run_nms("nms_empty_image", d, 0.1, 0.6)
+    # > 30000 candidates: exercises the top-max_nms cut (nms.py:61-63); scores are distinct w.h.p.
+    big = synthetic_detections(1, 3600, 10, seed=56, clusters=400)
+    big[..., 4] = 0.9 + 0.1 * big[..., 4]
+    big[..., 5:] = 0.2 + 0.8 * big[..., 5:]
+    run_nms("nms_over_max", big, 0.001, 0.6)
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    assign_cases()
+    loss_cases()
+    decode_cases()
+    nms_cases()
