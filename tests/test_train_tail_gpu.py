@@ -1,0 +1,134 @@
+"""GPU parity: CUDA target assignment + fused loss forward/backward, called through the C ABI
+(ctypes -> libkodb.so), against the golden vectors of the real reference and against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import _golden as G
+from object_detection_cib_b200 import synthetic as syn
+from object_detection_cib_b200.iou import IoUCalculator, IoUType
+from object_detection_cib_b200.label_assignment import Yolov5LabelAssigner
+from object_detection_cib_b200.loss import Yolov5Loss, Yolov5LossParams
+from object_detection_cib_b200.types import DetectionHeadResult, FeatureShape, default_anchor_info
+from oracle import assign as oa
+from oracle import loss as ol
+
+pytestmark = pytest.mark.gpu
+LEVELS = list(zip(syn.STRIDES, syn.ANCHORS_PX))
+DEV = "cuda:0"
+
+
+def _tt(targets, device="cpu"):
+    return [(torch.as_tensor(b).to(device), torch.as_tensor(l).to(device)) for b, l in targets]
+
+
+def _check_assignment(res, want_levels):
+    for r, w in zip(res, want_levels):
+        got = dict(samples=r.indices.samples, anchors=r.indices.anchors, grid_y=r.indices.grid_y,
+                   grid_x=r.indices.grid_x, labels=r.labels)
+        for k, v in got.items():
+            assert v.dtype == torch.long
+            assert np.array_equal(v.cpu().numpy(), w[k]), k
+        assert np.array_equal(r.gt_boxes.cpu().numpy().view(np.uint32), w["gt_boxes"].view(np.uint32))
+        assert np.array_equal(r.anchors.cpu().numpy().view(np.uint32), w["anchor_wh"].view(np.uint32))
+
+
+@pytest.mark.parametrize("name", G.names("assign_"))
+@pytest.mark.parametrize("where", ["cpu", DEV])
+def test_assign_golden(name, where):
+    g = G.load(name)
+    asg = Yolov5LabelAssigner(default_anchor_info(), threshold=float(g["threshold"][0]), device=DEV)
+    res = asg(FeatureShape(int(g["img_wh"][0]), int(g["img_wh"][1])), _tt(G.targets_of(g), where))
+    want = [{k: g[f"{ln}_{k}"] for k in ("samples", "anchors", "grid_y", "grid_x", "labels", "gt_boxes", "anchor_wh")}
+            for ln in G.LEVEL_NAMES]
+    _check_assignment(res, want)
+
+
+@pytest.mark.parametrize("B,S,nmax,dtype", [(64, 640, 10, torch.float32), (16, 1280, 40, torch.float32),
+                                            (7, 416, 72, torch.float64), (3, 96, 300, torch.float32)])
+def test_assign_vs_oracle_large(B, S, nmax, dtype):
+    targets = syn.make_targets(B, S, 10, seed=B * 7 + S, n_max=nmax, dtype=dtype, size_hi=S * 0.6)
+    # centres snapped to cell boundaries -> duplicate rows
+    b0, l0 = targets[0]
+    if b0.shape[0]:
+        c = ((b0[:, :2] + b0[:, 2:]) / 2 / 32).round() * 32
+        targets[0] = (torch.cat((c - 20, c + 20), 1).clamp(0, S - 1).to(dtype), l0)
+    res = Yolov5LabelAssigner(default_anchor_info(), device=DEV)(FeatureShape(S, S), targets)
+    want = oa.assign([(b.numpy(), l.numpy()) for b, l in targets], LEVELS, S, S)
+    _check_assignment(res, [w._asdict() for w in want])
+
+
+def _loss_module(hp, iou_type, weights):
+    return Yolov5Loss(Yolov5LabelAssigner(default_anchor_info()), hp, IoUCalculator(IoUType(iou_type), 1e-7), weights)
+
+
+def _run_cuda_loss(heads_cpu, targets, S, hp, iou_type, weights, upstream=None):
+    leaves = []
+    for lv in heads_cpu:
+        leaves.append(DetectionHeadResult(*[t.to(DEV).detach().requires_grad_(True) for t in lv]))
+    mod = _loss_module(hp, iou_type, weights)
+    res = mod(FeatureShape(S, S), leaves, targets)
+    B = heads_cpu[0][0].shape[0]
+    u = upstream or (B, B, B)
+    total = u[0] * res.localization + u[1] * res.objectness + u[2] * res.classification
+    total.backward()
+    losses = np.array([res.localization.item(), res.objectness.item(), res.classification.item()], np.float32)
+    grads = [[t.grad.cpu() for t in lv] for lv in leaves]
+    return losses, grads, mod
+
+
+def _assert_grads_close(got, want, rtol=1e-5):
+    for lv_g, lv_w in zip(got, want):
+        for a, b in zip(lv_g, lv_w):
+            a, b = a.numpy(), b.numpy()
+            assert a.shape == b.shape
+            scale = float(np.abs(b).max()) or 1.0
+            # 1e-5 relative, with an absolute floor of 1e-5 x the tensor's largest gradient for
+            # entries that are sums of cancelling terms
+            np.testing.assert_allclose(a, b, rtol=rtol, atol=rtol * scale)
+
+
+@pytest.mark.parametrize("name", G.names("loss_"))
+def test_loss_golden(name):
+    g = G.load(name)
+    B, S, C = (int(v) for v in g["meta"])
+    hp = Yolov5LossParams(*[float(v) for v in g["hparams"]])
+    w = g["weights"].tolist() if g["weights"].size else None
+    losses, grads, _ = _run_cuda_loss(G.heads_of(g), _tt(G.targets_of(g)), S, hp, str(g["iou_type"][0]), w)
+    np.testing.assert_allclose(losses, g["losses"], rtol=1e-5, atol=0, equal_nan=True)
+    _assert_grads_close(grads, G.heads_of(g, grads=True))
+
+
+@pytest.mark.parametrize("B,S,C,upstream", [(8, 640, 10, None), (4, 320, 80, (1.0, 1.0, 1.0)),
+                                            (3, 416, 10, (2.0, 0.5, 3.0))])
+def test_loss_vs_oracle(B, S, C, upstream):
+    heads = syn.make_head(B, S, C, seed=S + C)
+    targets = syn.make_targets(B, S, C, seed=S, n_max=10, empty_images=(1,))
+    w = syn.readme_class_weights() if C == 10 else None
+    hp = Yolov5LossParams.get_default()
+    losses, grads, mod = _run_cuda_loss(heads, targets, S, hp, "ciou", w, upstream)
+    asg = oa.assign([(b.numpy(), l.numpy()) for b, l in targets], LEVELS, S, S)
+    assert mod.last_num_assigned.tolist() == [a.samples.shape[0] for a in asg]
+    want_l, want_g = ol.loss_forward_backward(heads, asg, S, ol.LossHParams(*hp), "ciou", 1e-7, w,
+                                              upstream=upstream or (B, B, B))
+    np.testing.assert_allclose(losses, np.array([float(v) for v in want_l], np.float32), rtol=1e-5, equal_nan=True)
+    _assert_grads_close(grads, want_g)
+
+
+def test_loss_no_grad_and_determinism():
+    B, S, C = 4, 256, 10
+    heads = [DetectionHeadResult(*[t.to(DEV) for t in lv]) for lv in syn.make_head(B, S, C, seed=1)]
+    targets = syn.make_targets(B, S, C, seed=2)
+    mod = _loss_module(Yolov5LossParams.get_default(), "ciou", None)
+    with torch.no_grad():
+        a = mod(FeatureShape(S, S), heads, targets)
+        b = mod(FeatureShape(S, S), heads, targets)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))  # fixed-order fp64 reduction
+    assert not a.localization.requires_grad
+
+
+def test_fails_loudly_on_cpu_tensors():
+    heads = syn.make_head(1, 64, 3, seed=1)
+    mod = _loss_module(Yolov5LossParams.get_default(), "ciou", None)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        mod(FeatureShape(64, 64), heads, syn.make_targets(1, 64, 3))
