@@ -1,0 +1,204 @@
+"""GPU parity of the eval tail through the C ABI: decode, NMS keep indices (bit-exact), COCO matching
+TP/FP flags (bit-exact vs the oracle restatement) and AP (1e-4 abs)."""
+import numpy as np
+import pytest
+import torch
+
+import _golden as G
+from object_detection_cib_b200 import nms as N
+from object_detection_cib_b200 import synthetic as syn
+from object_detection_cib_b200.map_eval import DeviceCocoMapEvaluator
+from object_detection_cib_b200.types import DetectionHeadResult, FeatureShape, default_anchor_info
+from oracle import coco_map as om
+from oracle import decode as od
+from oracle import nms as on
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+LEVELS = list(zip(syn.STRIDES, syn.ANCHORS_PX))
+
+
+def _to_dev(heads):
+    return [DetectionHeadResult(*[t.to(DEV) for t in lv]) for lv in heads]
+
+
+def _ulp_diff(a, b):
+    ai = a.view(np.int32).astype(np.int64)
+    bi = b.view(np.int32).astype(np.int64)
+    return np.abs(ai - bi)
+
+
+@pytest.mark.parametrize("name", G.names("decode_"))
+def test_decode_golden(name):
+    g = G.load(name)
+    B, S, C = (int(v) for v in g["meta"])
+    det = N.get_detections(FeatureShape(S, S), _to_dev(G.heads_of(g)), default_anchor_info()).cpu().numpy()
+    want = g["detections"]
+    assert det.shape == want.shape
+    # fp32 transcendental (expf) differs from the CPU's vectorised exp by a few ulp
+    np.testing.assert_allclose(det, want, rtol=2e-6, atol=2e-6)
+    assert _ulp_diff(det[..., 4:], want[..., 4:]).max() <= 8
+
+
+def _check_nms_against(res, ref_images, max_det=300):
+    counts = res.counts.cpu().numpy()
+    dets = res.dets.cpu().numpy()
+    keep = res.keep_idx.cpu().numpy()
+    for b, r in enumerate(ref_images):
+        assert counts[b] == r.dets.shape[0], (b, counts[b], r.dets.shape[0])
+        n = counts[b]
+        assert np.array_equal(keep[b, :n], r.keep), b
+        assert np.array_equal(dets[b, :n].view(np.uint32), r.dets.view(np.uint32)), b
+        assert not dets[b, n:].any() and (keep[b, n:] == -1).all()
+
+
+@pytest.mark.parametrize("name", G.names("nms_"))
+def test_nms_golden(name):
+    g = G.load(name)
+    conf, iou = (float(v) for v in g["conf_iou"])
+    classes = g["classes"].tolist() if g["classes"].size else None
+    det = torch.from_numpy(g["detections"]).to(DEV)
+    res = N.nms_padded(det, conf, iou, classes)
+    counts = res.counts.cpu().numpy()
+    assert counts.tolist() == g["counts"].tolist()
+    for b in range(det.shape[0]):
+        n = counts[b]
+        assert np.array_equal(res.keep_idx[b, :n].cpu().numpy(), g[f"keep_{b}"]), (name, b)
+        assert np.array_equal(res.dets[b, :n].cpu().numpy().view(np.uint32), g[f"out_{b}"].view(np.uint32)), (name, b)
+        if g[f"ncand_{b}"][0]:
+            assert min(int(res.num_candidates[b]), 30000) == int(g[f"ncand_{b}"][0])
+    # the list-returning drop-in
+    lst = N.non_max_suppression(det, conf, iou, classes)
+    assert [int(t.shape[0]) for t in lst] == g["counts"].tolist()
+
+
+def _clustered(B, N_, C, seed, tie_every=0):
+    g = torch.Generator().manual_seed(seed)
+    cen = torch.rand(B, 60, 2, generator=g) * 640
+    size = 20 + torch.rand(B, 60, 2, generator=g) * 150
+    which = torch.randint(0, 60, (B, N_), generator=g)
+    c = torch.gather(cen, 1, which[..., None].expand(-1, -1, 2)) + torch.randn(B, N_, 2, generator=g) * 6
+    s = torch.gather(size, 1, which[..., None].expand(-1, -1, 2)) * (1 + 0.15 * torch.randn(B, N_, 2, generator=g)).abs()
+    obj = torch.rand(B, N_, 1, generator=g) ** 2
+    cls = torch.rand(B, N_, C, generator=g) ** 3
+    if tie_every:
+        obj[:, ::tie_every] = 0.5
+        cls[:, ::tie_every] = 0.25
+    return torch.cat((c - s / 2, c + s / 2, obj, cls), -1).float()
+
+
+@pytest.mark.parametrize("B,N_,C,conf,iou,tie", [(3, 3000, 10, 0.001, 0.6, 5), (2, 5000, 3, 0.05, 0.3, 0),
+                                                  (2, 2500, 80, 0.01, 0.6, 0), (1, 9000, 1, 0.001, 0.5, 3)])
+def test_nms_vs_oracle(B, N_, C, conf, iou, tie, oracle_lib):
+    det = _clustered(B, N_, C, seed=N_ + C, tie_every=tie)
+    res = N.nms_padded(det.to(DEV), conf, iou)
+    _check_nms_against(res, on.non_max_suppression(det.numpy(), conf, iou))
+
+
+def test_nms_all_ties_refinement(oracle_lib):
+    """Thousands of identical scores overflow one histogram bin: exercises the radix refinement."""
+    det = _clustered(1, 6000, 2, seed=9)
+    det[..., 4] = 0.5
+    det[..., 5:] = 0.5
+    res = N.nms_padded(det.to(DEV), 0.1, 0.6)
+    _check_nms_against(res, on.non_max_suppression(det.numpy(), 0.1, 0.6))
+
+
+@pytest.mark.parametrize("B,S,C,shift", [(4, 640, 10, 0.0), (2, 416, 10, 2.0), (2, 320, 80, 1.0)])
+def test_fused_eval_tail_equals_decode_then_nms(B, S, C, shift, oracle_lib):
+    """fused(head) == reference NMS applied to our decode of the same head (bit-exact keeps), and our
+    decode == the oracle decode within fp32 tolerance."""
+    heads = syn.make_head(B, S, C, seed=S + C, obj_shift=shift)
+    targets = syn.make_targets(B, S, C, seed=3)
+    syn.inject_ground_truth(heads, targets, S)
+    dh = _to_dev(heads)
+    shape, info = FeatureShape(S, S), default_anchor_info()
+    det = N.get_detections(shape, dh, info)
+    np.testing.assert_allclose(det.cpu().numpy(), od.get_detections(heads, LEVELS).numpy(), rtol=2e-6, atol=2e-5)
+    fused = N.eval_tail(shape, dh, info, 0.001, 0.6)
+    _check_nms_against(fused, on.non_max_suppression(det.cpu().numpy(), 0.001, 0.6))
+    # and the two CUDA entry points agree with each other
+    two_step = N.nms_padded(det, 0.001, 0.6)
+    assert torch.equal(fused.dets, two_step.dets) and torch.equal(fused.keep_idx, two_step.keep_idx)
+
+
+def _match_oracle(dets_list, targets, C):
+    o = om.CocoMapOracle(C)
+    ms = []
+    for d, (gb, gl) in zip(dets_list, targets):
+        m = om.match_image(d, gb.numpy(), gl.numpy(), C)
+        ms.append(m)
+        o._matches.append(m)
+    return ms, o.get_report()
+
+
+@pytest.mark.parametrize("B,S,C,dtype", [(6, 640, 10, torch.float32), (3, 320, 80, torch.float64)])
+def test_matching_and_ap(B, S, C, dtype, oracle_lib):
+    heads = syn.make_head(B, S, C, seed=S * 3 + C)
+    targets = syn.make_targets(B, S, C, seed=5, n_min=1, n_max=12, dtype=dtype, empty_images=(2,))
+    syn.inject_ground_truth(heads, targets, S, fraction=0.7)
+    ev = DeviceCocoMapEvaluator(C, device=DEV)
+    res, rec = N.eval_tail(FeatureShape(S, S), _to_dev(heads), default_anchor_info(), 0.001, 0.6, targets=targets,
+                           gt_count=ev.gt_count)
+    ev.add_records(rec)
+    counts = res.counts.cpu().numpy()
+    dets = res.dets.cpu().numpy()
+    ms, want = _match_oracle([dets[b, :counts[b]] for b in range(B)], targets, C)
+    tp = rec.tp.cpu().numpy()
+    n_tp = 0
+    for b, m in enumerate(ms):
+        bits = (m.tp * (1 << np.arange(4))[None, :]).sum(1).astype(np.uint8)
+        assert np.array_equal(tp[b, :counts[b]], bits), b  # TP/FP flags bit-exact
+        assert np.array_equal(rec.cls[b, :counts[b]].cpu().numpy(), m.cls)
+        n_tp += int(m.tp[:, 1].sum())
+    assert n_tp > 0, "synthetic set must contain true positives"
+    assert ev.gt_count.cpu().numpy().tolist() == np.sum([m.gt_count for m in ms], 0).tolist()
+    got = ev.get_report()
+    for k in ("avg_mAP", "mAP_30", "mAP_50", "mAP_75", "mAP_90"):
+        assert abs(got[k] - want[k]) < 1e-4, (k, got[k], want[k])
+    assert got["tag_wise_AP_50"].keys() == want["tag_wise_AP_50"].keys()
+    for k, v in want["tag_wise_AP_50"].items():
+        assert abs(got["tag_wise_AP_50"][k] - v) < 1e-4
+    # the reference-protocol entry point (python lists) gives the same report
+    ev2 = DeviceCocoMapEvaluator(C, device=DEV)
+    preds = [[(float(r[5]), float(r[4]), float(r[0]), float(r[1]), float(r[2]), float(r[3])) for r in dets[b, :counts[b]]]
+             for b in range(B)]
+    gts = [[(int(l), *[float(v) for v in bx]) for bx, l in zip(gb, gl)] for gb, gl in targets]
+    ev2.add_predictions(preds, gts)
+    got2 = ev2.get_report()
+    assert abs(got2["avg_mAP"] - want["avg_mAP"]) < 1e-4
+
+
+def test_ap_accumulate_many_images(oracle_lib):
+    """Accumulation over several batches with score ties across images (stable order matters)."""
+    C, B = 5, 40
+    rng = np.random.default_rng(11)
+    ev = DeviceCocoMapEvaluator(C, device=DEV)
+    orc = om.CocoMapOracle(C)
+    for step in range(3):
+        dets = np.zeros((B, 300, 6), np.float32)
+        counts = rng.integers(0, 60, B).astype(np.int32)
+        targets = []
+        for b in range(B):
+            n = counts[b]
+            ng = int(rng.integers(0, 6))
+            gb = rng.uniform(0, 500, (ng, 2))
+            gb = np.concatenate([gb, gb + rng.uniform(10, 120, (ng, 2))], 1)
+            gl = rng.integers(0, C, ng)
+            c = rng.uniform(0, 500, (n, 2))
+            d = np.concatenate([c, c + rng.uniform(10, 120, (n, 2))], 1)
+            if ng and n:
+                pick = rng.integers(0, ng, n // 2)
+                d[: n // 2] = gb[pick] + rng.normal(0, 4, (n // 2, 4))
+            sc = np.sort(np.round(rng.uniform(0.01, 1, n), 2))[::-1]  # descending, many ties
+            dets[b, :n, :4] = d
+            dets[b, :n, 4] = sc
+            dets[b, :n, 5] = rng.integers(0, C, n)
+            if ng and n:
+                dets[b, : n // 2, 5] = gl[pick]
+            targets.append((torch.from_numpy(gb), torch.from_numpy(gl)))
+            orc.add_image(dets[b, :n], gb, gl)
+        ev.add_detections(torch.from_numpy(dets).to(DEV), torch.from_numpy(counts), targets)
+    got, want = ev.get_report(), orc.get_report()
+    for k in ("avg_mAP", "mAP_30", "mAP_50", "mAP_75", "mAP_90"):
+        assert abs(got[k] - want[k]) < 1e-9, (k, got[k], want[k])
