@@ -1,0 +1,497 @@
+#!/usr/bin/env python
+"""Benchmark of the YOLOv5s detection tail (BASELINE.json metric: head+loss+NMS images/s).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port)
+
+One "step" = one pass of the hot path over one batch of `--batch` images per GPU (default: config[1] of
+BASELINE.json, 64 images/GPU at 640x640, 10 classes, class-weighted loss):
+  train tail : target assignment + CIoU/objectness/class-weighted BCE loss, forward AND backward
+               (kodb_train_tail, one kernel)
+  eval tail  : sigmoid/grid/anchor decode + conf 0.001 filter + class-offset NMS (IoU 0.6, 300/img)
+               + per-class COCO matching (kodb_eval_tail, two kernels)
+`value` is device-resident throughput (CUDA events, max over ranks); `e2e` goes through the public
+Python drop-ins with host buffers (H2D of the head maps and targets, D2H of losses/detections/records
+inside the timed region).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "yolov5s_tail_images_per_s"
+UNIT = "images/s"
+NSETS = 3  # rotating input sets: 3 x (96.8 MB head + 96.8 MB grads) >> 126 MB L2
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU")
+    ap.add_argument("--img", type=int, default=640)
+    ap.add_argument("--classes", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=8, help="images in the cpu_baseline sample")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"yolov5s detection tail, {a.batch} img/GPU {a.img}x{a.img}, {a.classes} classes: train tail "
+            f"(assign + CIoU/obj/cls loss fwd+bwd, class weights) + eval tail (decode, conf 0.001, NMS 0.6, "
+            f"mAP matching); synthetic Zipf boxes")
+
+
+def algorithmic_bytes(a):
+    """per-image algorithmic bytes of the two tails."""
+    ac = sum(3 * (a.img // s) ** 2 for s in (8, 16, 32))
+    train = 4 * ac * (1 + 5 + a.classes)
+    evalb = 4 * ac * (5 + a.classes) + 300 * (6 * 4 + 8)
+    return ac, train, evalb
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi) during the loaded regions
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i",
+                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.rows:
+            if not (t0 - 0.05 <= ts <= t1 + 0.1):
+                continue
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for name, v in zip(self.NAMES, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    from object_detection_cib_b200 import _host as H
+    from object_detection_cib_b200 import _lib as L
+    from object_detection_cib_b200 import nms as N
+    from object_detection_cib_b200 import synthetic as syn
+    from object_detection_cib_b200.iou import IoUCalculator, IoUType
+    from object_detection_cib_b200.label_assignment import Yolov5LabelAssigner
+    from object_detection_cib_b200.loss import Yolov5Loss, Yolov5LossParams, launch_train_tail
+    from object_detection_cib_b200.map_eval import DeviceCocoMapEvaluator
+    from object_detection_cib_b200.types import DetectionHeadResult, FeatureShape, default_anchor_info
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl=ours) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = L.lib()
+    B, S, Cn = a.batch, a.img, a.classes
+    shape, info = FeatureShape(S, S), default_anchor_info()
+    weights = syn.readme_class_weights() if Cn == 10 else None
+    loss_mod = Yolov5Loss(Yolov5LabelAssigner(info), Yolov5LossParams.get_default(), IoUCalculator(IoUType.ciou, 1e-7),
+                          weights)
+    evaluator = DeviceCocoMapEvaluator(Cn, device=dev)
+
+    # ---- NSETS rotating input sets, resident in HBM ---------------------------------------------------
+    sets = []
+    for s in range(NSETS):
+        seed = 2023 + 17 * s + 101 * rank
+        heads = syn.make_head(B, S, Cn, seed=seed, device=dev)
+        targets = syn.make_targets(B, S, Cn, seed=seed, n_min=0, n_max=10)
+        syn.inject_ground_truth(heads, targets, S, fraction=0.3, seed=seed)
+        net = [DetectionHeadResult(*lv) for lv in heads]
+        plan = loss_mod.plan(shape, net, targets)
+        grads = [H.alloc_planar_like(t) for t in plan.heads.tensors]
+        losses = torch.zeros(3, dtype=torch.float32, device=dev)
+        nass = torch.zeros(3, dtype=torch.int32, device=dev)
+        levels = H.level_cfgs(info, S, S)
+        rows = sum(lv.num_anchors * lv.H * lv.W for lv in levels)
+        cfg = N._nms_cfg(Cn, 0.001, 0.6, None, N.MAX_DET, N.MAX_NMS)
+        res, out = N._alloc_out(B, N.MAX_DET, dev)
+        match = N._alloc_match(B, N.MAX_DET, evaluator.gt_count, res.counts, dev, N.IOU_THRESHOLDS)
+        ws = H.workspace(f"eval{s}", dev, lib.kodb_eval_workspace_bytes(B, rows, Cn))
+        sets.append(dict(heads=heads, targets=targets, net=net, plan=plan, grads=grads, losses=losses, nass=nass,
+                         levels=levels, cfg=cfg, res=res, out=out, match=match, ws=ws, gstruct=H.grad_structs(grads)))
+    hint = (float(B),) * 3
+    up = (C.c_float * 3)(*hint)
+    errs = []
+
+    def train_call(st):
+        p = st["plan"]
+        rc = lib.kodb_train_tail(p.heads.structs, p.levels, C.byref(p.packed.struct), C.byref(p.cfg),
+                                 p.pos_weight.data_ptr() if p.pos_weight is not None else None, up, None, 0,
+                                 st["gstruct"], st["losses"].data_ptr(), st["nass"].data_ptr(), p.workspace.data_ptr(),
+                                 p.workspace.numel(), H.stream_ptr(dev))
+        if rc:
+            errs.append(("train", rc))
+
+    def eval_call(st, stage_mask=0):
+        p = st["plan"]
+        st["cfg"].stage_mask = stage_mask
+        rc = lib.kodb_eval_tail(p.heads.structs, st["levels"], B, C.byref(st["cfg"]), C.byref(st["out"]),
+                                C.byref(p.packed.struct), C.byref(st["match"].struct), st["ws"].data_ptr(),
+                                st["ws"].numel(), H.stream_ptr(dev))
+        st["cfg"].stage_mask = 0
+        if rc:
+            errs.append(("eval", rc))
+
+    def step_eager(i):
+        st = sets[i % NSETS]
+        train_call(st)
+        eval_call(st)
+
+    LAUNCHES_PER_STEP = 3  # train_tail_kernel, cand_kernel<planar>, select_nms_kernel
+
+    # ---- CUDA graphs: one per input set -----------------------------------------------------------------
+    for i in range(NSETS):  # first launches set per-device function attributes (not capturable)
+        step_eager(i)
+    torch.cuda.synchronize(dev)
+    graphs = None
+    if not a.no_graph:
+        try:
+            graphs = []
+            for i in range(NSETS):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    step_eager(i)
+                graphs.append(g)
+        except Exception as e:  # pragma: no cover
+            sys.stderr.write(f"[bench] CUDA graph capture failed ({e}); timing eager launches\n")
+            graphs = None
+            torch.cuda.synchronize(dev)
+
+    def step(i):
+        if graphs is not None:
+            graphs[i % NSETS].replay()
+        else:
+            step_eager(i)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.15)
+
+    # ---- warm-up + the timed region: EXACTLY K steps ------------------------------------------------------
+    for i in range(max(a.warmup, 3)):
+        step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_load0 = time.time()
+    e0.record()
+    for i in range(a.steps):
+        step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_total = float(tms.item())
+    ms_per_step = ms_total / a.steps
+    value = world * B * a.steps / (ms_total / 1e3)
+
+    # ---- instrumented pass: per-kernel device time (eager launches, events between the kernels) ---------
+    n_inst = max(a.steps, 50)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(n_inst)]
+    for i in range(3):
+        step_eager(i)
+    torch.cuda.synchronize(dev)
+    for i in range(n_inst):
+        st = sets[i % NSETS]
+        evs[i][0].record()
+        train_call(st)
+        evs[i][1].record()
+        eval_call(st, 1)
+        evs[i][2].record()
+        eval_call(st, 2)
+        evs[i][3].record()
+    torch.cuda.synchronize(dev)
+    t_load1 = time.time()
+    t_train = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)
+    t_cand = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
+    t_sel = statistics.mean(e[2].elapsed_time(e[3]) for e in evs)
+
+    # ---- end-to-end through the public drop-in API with HOST buffers -----------------------------------
+    e2e = None
+    if not a.no_e2e:
+        st = sets[0]
+        host_heads = [[t.permute(0, 1, 4, 2, 3).contiguous().cpu().pin_memory() for t in lv] for lv in st["heads"]]
+        host_out = dict(
+            losses=torch.empty(3, dtype=torch.float32).pin_memory(),
+            dets=torch.empty((B, N.MAX_DET, 6), dtype=torch.float32).pin_memory(),
+            counts=torch.empty((B,), dtype=torch.int32).pin_memory(),
+            tp=torch.empty((B, N.MAX_DET), dtype=torch.uint8).pin_memory())
+        h2d = sum(t.numel() * 4 for lv in host_heads for t in lv) + sum(b.numel() * 4 + l.numel() * 8 for b, l in st["targets"])
+        d2h = sum(t.numel() * t.element_size() for t in host_out.values())
+        ev_e2e = DeviceCocoMapEvaluator(Cn, device=dev)
+
+        def e2e_step():
+            net = []
+            for lv in host_heads:
+                d = [t.to(dev, non_blocking=True).permute(0, 1, 3, 4, 2).requires_grad_(True) for t in lv]
+                net.append(DetectionHeadResult(*d))
+            r = loss_mod(shape, net, st["targets"])  # packs + uploads the targets
+            total = B * (r.localization + r.classification + r.objectness)  # exp.py:124-130
+            total.backward()
+            res, rec = N.eval_tail(shape, net, info, 0.001, 0.6, targets=st["targets"], gt_count=ev_e2e.gt_count)
+            host_out["losses"].copy_(torch.stack((r.localization, r.objectness, r.classification)).detach(), non_blocking=True)
+            host_out["dets"].copy_(res.dets, non_blocking=True)
+            host_out["counts"].copy_(res.counts, non_blocking=True)
+            host_out["tp"].copy_(rec.tp, non_blocking=True)
+            torch.cuda.synchronize(dev)  # the step's results are on the host
+
+        n_e2e = max(3, min(a.steps, 30))
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B * n_e2e / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "steps": n_e2e,
+               "api": "Yolov5Loss.forward+backward, nms.eval_tail (pinned host head maps -> device -> pinned host results)"}
+
+    # ---- epoch-end exchange (the only collective of the path): gather records + global AP ---------------
+    for st in sets:
+        evaluator.add_records(st["match"].records)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    report = evaluator.get_report()
+    epoch_end_ms = (time.perf_counter() - t0) * 1e3
+
+    clocks = sampler.stop(t_load0, t_load1) if rank == 0 else None
+    if errs:
+        raise RuntimeError(f"C-ABI calls failed: {errs[:3]}")
+    if rank == 0:
+        ac, b_train, b_eval = algorithmic_bytes(a)
+        peak, peak_src = measured_peak_gbs()
+        kernels = {
+            "train_tail_kernel": (t_train, b_train * B),
+            "cand_kernel+select_nms_kernel (eval tail)": (t_cand + t_sel, b_eval * B),
+        }
+        dom = max(kernels, key=lambda k: kernels[k][0])
+        t_dom, bytes_dom = kernels[dom]
+        ach = bytes_dom / (t_dom * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "images_per_gpu": B, "global_batch": B * world, "img": S,
+                       "classes": Cn, "parallelism": f"dp{world} (shard by image, no data-path collective)",
+                       "l2": f"inputs rotate over {NSETS} sets ({NSETS}x{(b_eval * B) / 1e6:.0f} MB head + grads) > 126 MB L2",
+                       "launch": "cuda-graph replay" if graphs is not None else "eager async launches"},
+            "gpu_launches": LAUNCHES_PER_STEP * a.steps,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bytes_dom, "kernel_ms": t_dom},
+            "stages_ms": {"train_tail_kernel": t_train, "cand_kernel": t_cand, "select_nms_kernel": t_sel,
+                          "note": "eager instrumented pass, CUDA events between launches"},
+            "roofline_stages": {
+                "train_tail": {"achieved_gbs": b_train * B / (t_train * 1e-3) / 1e9, "frac": b_train * B / (t_train * 1e-3) / 1e9 / peak},
+                "eval_tail": {"achieved_gbs": b_eval * B / ((t_cand + t_sel) * 1e-3) / 1e9,
+                              "frac": b_eval * B / ((t_cand + t_sel) * 1e-3) / 1e9 / peak},
+                "step": {"achieved_gbs": (b_train + b_eval) * B / (ms_per_step * 1e-3) / 1e9,
+                         "frac": (b_train + b_eval) * B / (ms_per_step * 1e-3) / 1e9 / peak}},
+            "e2e": e2e, "clocks": clocks, "epoch_end_ms": epoch_end_ms,
+            "map_report": {k: report[k] for k in ("avg_mAP", "mAP_50")},
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(a, a.cpu_sample)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU legs: the oracle port of the reference path (the ONLY place bench.py executes oracle/)
+# ------------------------------------------------------------------------------------------------------
+def _cpu_inputs(a, n_img, seed=2023):
+    import torch
+
+    from object_detection_cib_b200 import synthetic as syn
+
+    heads = syn.make_head(n_img, a.img, a.classes, seed=seed)
+    targets = syn.make_targets(n_img, a.img, a.classes, seed=seed, n_min=0, n_max=10)
+    syn.inject_ground_truth(heads, targets, a.img, fraction=0.3, seed=seed)
+    return heads, targets
+
+
+def _cpu_step(a, heads, targets, nms_backend):
+    """One pass of the reference algorithm over `heads`: train tail fwd+bwd, decode, NMS, matching."""
+    import numpy as np
+
+    from object_detection_cib_b200 import synthetic as syn
+    from oracle import assign as oa
+    from oracle import coco_map as om
+    from oracle import decode as od
+    from oracle import loss as ol
+    from oracle import nms as on
+
+    levels = list(zip(syn.STRIDES, syn.ANCHORS_PX))
+    n = heads[0][0].shape[0]
+    asg = oa.assign([(b.numpy(), l.numpy()) for b, l in targets], levels, a.img, a.img)
+    w = syn.readme_class_weights() if a.classes == 10 else None
+    ol.loss_forward_backward(heads, asg, a.img, ol.LossHParams(), "ciou", 1e-7, w, upstream=(n, n, n))
+    det = od.get_detections(heads, levels).numpy()
+    res = on.non_max_suppression(det, 0.001, 0.6, backend=nms_backend)
+    for r, (gb, gl) in zip(res, targets):
+        om.match_image(r.dets, gb.numpy(), gl.numpy(), a.classes)
+
+
+def _nms_backend():
+    try:
+        import torchvision  # noqa: F401
+
+        return "torchvision"
+    except Exception:
+        return "c"
+
+
+def cpu_baseline(a, n_img):
+    import torch
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    backend = _nms_backend()
+    heads, targets = _cpu_inputs(a, n_img)
+    t0 = time.perf_counter()
+    _cpu_step(a, heads, targets, backend)
+    dt = time.perf_counter() - t0
+    return {"value": n_img / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n_img} images of the step's workload (oracle port: assign + loss fwd/bwd via torch CPU "
+                      f"autograd, decode, {backend} greedy NMS conf 0.001 / IoU 0.6, COCO matching), {dt:.1f} s",
+            "seconds": dt}
+
+
+def run_reference(a):
+    """Reference arm: the reference's own CPU implementation of the path.  The reference is pure Python
+    (no compiled path, nothing to build into oracle/_ref) and /root/reference does not travel to the GPU
+    box, so this times the oracle port: the same ATen ops through torch CPU + torchvision's CPU NMS."""
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if rank != 0:
+        return
+    import torch
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    backend = _nms_backend()
+    total = a.steps + a.warmup
+    n_img = 2 if total <= 12 else 1  # bounded sample: ~1.5-3 s of CPU work per image (O(n^2) NMS)
+    heads, targets = _cpu_inputs(a, n_img)
+    for _ in range(min(a.warmup, 1)):  # the CPU path has no warm-up effect worth more than one pass
+        _cpu_step(a, heads, targets, backend)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(a.steps):
+        _cpu_step(a, heads, targets, backend)
+        done += 1
+        if time.perf_counter() - t0 > 240 and done >= 3:  # keep the whole run within a few minutes
+            break
+    dt = time.perf_counter() - t0
+    value = n_img * done / dt
+    sample = (f"{n_img} image(s) per step of the {a.batch}-image batch, {done} of {a.steps} requested steps timed "
+              f"(oracle port on torch CPU, {backend} NMS)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": done,
+        "warmup": min(a.warmup, 1), "ms_per_step": dt / done * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "images_per_step": n_img, "img": a.img, "classes": a.classes},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

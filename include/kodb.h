@@ -158,6 +158,8 @@ typedef struct kodb_nms_cfg {
     int32_t max_nms;    /* 30000 */
     int32_t num_classes;
     uint32_t class_mask[KODB_MAX_CLASSES / 32]; /* `classes` filter; all ones = None */
+    int32_t stage_mask; /* 0 or 3 = both kernels; 1 = candidate kernel only; 2 = select/NMS kernel only
+                           (lets a profiler put an event between the two launches of one call) */
 } kodb_nms_cfg;
 
 /* Outputs of the NMS stage; dets rows beyond counts[b] are zero. */

@@ -68,7 +68,7 @@ class NmsCfg(C.Structure):
     _fields_ = [
         ("conf_thres", C.c_float), ("iou_thres", C.c_double), ("max_wh", C.c_float),
         ("max_det", C.c_int32), ("max_nms", C.c_int32), ("num_classes", C.c_int32),
-        ("class_mask", C.c_uint32 * (MAX_CLASSES // 32)),
+        ("class_mask", C.c_uint32 * (MAX_CLASSES // 32)), ("stage_mask", C.c_int32),
     ]
 
 

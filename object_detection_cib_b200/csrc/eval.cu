@@ -608,8 +608,14 @@ static int setup_match(EvalParams& p, const kodb_targets* gt, const kodb_match_o
 
 static int launch_select(const EvalParams& p, cudaStream_t st) {
     const size_t smem = sizeof(NmsSmem) > sizeof(MatchSmem) ? sizeof(NmsSmem) : sizeof(MatchSmem);
-    if (cudaFuncSetAttribute(select_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-        return KODB_ERR_LAUNCH;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        if (cudaFuncSetAttribute(select_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return KODB_ERR_LAUNCH;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
     select_nms_kernel<<<p.B, NMS_THREADS, smem, st>>>(p);
     KODB_CHECK_LAUNCH();
     return KODB_OK;
@@ -645,9 +651,12 @@ extern "C" int kodb_eval_tail(const kodb_head_level* heads_h, const kodb_level_c
     if ((rc = carve_ws(p, workspace, workspace_bytes)) != KODB_OK) return rc;
     if ((rc = setup_match(p, gt_h, match_h)) != KODB_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    cand_kernel<true><<<dim3(tiles, batch), EV_TILE, 0, st>>>(p);
-    KODB_CHECK_LAUNCH();
-    return launch_select(p, st);
+    const int stages = cfg_h->stage_mask ? cfg_h->stage_mask : 3;
+    if (stages & 1) {
+        cand_kernel<true><<<dim3(tiles, batch), EV_TILE, 0, st>>>(p);
+        KODB_CHECK_LAUNCH();
+    }
+    return (stages & 2) ? launch_select(p, st) : KODB_OK;
 }
 
 extern "C" int kodb_nms(const float* detections, int32_t batch, int64_t rows, const kodb_nms_cfg* cfg_h,
@@ -670,9 +679,12 @@ extern "C" int kodb_nms(const float* detections, int32_t batch, int64_t rows, co
     if ((rc = carve_ws(p, workspace, workspace_bytes)) != KODB_OK) return rc;
     if ((rc = setup_match(p, gt_h, match_h)) != KODB_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    cand_kernel<false><<<dim3(p.tiles_per_image, batch), EV_TILE, 0, st>>>(p);
-    KODB_CHECK_LAUNCH();
-    return launch_select(p, st);
+    const int stages = cfg_h->stage_mask ? cfg_h->stage_mask : 3;
+    if (stages & 1) {
+        cand_kernel<false><<<dim3(p.tiles_per_image, batch), EV_TILE, 0, st>>>(p);
+        KODB_CHECK_LAUNCH();
+    }
+    return (stages & 2) ? launch_select(p, st) : KODB_OK;
 }
 
 extern "C" int kodb_map_match(const float* dets, const int32_t* counts, int32_t batch, int32_t max_det,
@@ -683,8 +695,14 @@ extern "C" int kodb_map_match(const float* dets, const int32_t* counts, int32_t 
         return KODB_ERR_INVALID_ARGUMENT;
     if (gt_h->batch != batch) return KODB_ERR_INVALID_ARGUMENT;
     if (gt_h->max_per_image > GT_CAP) return KODB_ERR_CAPACITY;
-    if (cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MatchSmem)) != cudaSuccess)
-        return KODB_ERR_LAUNCH;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        if (cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MatchSmem)) != cudaSuccess)
+            return KODB_ERR_LAUNCH;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
     match_kernel<<<batch, NMS_THREADS, sizeof(MatchSmem), (cudaStream_t)stream>>>(
         dets, counts, num_classes, max_det, gt_h->boxes, gt_h->labels, gt_h->img_offsets, gt_h->boxes_dtype, *match_h);
     KODB_CHECK_LAUNCH();

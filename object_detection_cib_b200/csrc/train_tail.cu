@@ -492,19 +492,29 @@ extern "C" int kodb_train_tail(const kodb_head_level* heads_h, const kodb_level_
     p.partials = reinterpret_cast<double*>(workspace);
     p.counter = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(workspace) + (size_t)kTrainMaxGrid * 9 * sizeof(double));
 
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (num_sms <= 0) num_sms = 148;
+    // launch geometry is cached per device (no attribute / occupancy queries on the steady-state path,
+    // which also keeps the call capturable into a CUDA graph after one warm-up launch)
+    static int c_sms[64] = {0}, c_per_sm[64] = {0};
+    static size_t c_smem[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return KODB_ERR_UNSUPPORTED;
+    if (c_sms[dev] == 0 || c_smem[dev] != smem) {
+        int sms = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+        if (smem > 48 * 1024 &&
+            cudaFuncSetAttribute(train_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return KODB_ERR_LAUNCH;
+        int occ = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, train_tail_kernel, TT_THREADS, smem);
+        if (occ < 1) occ = 1;
+        if (occ > 8) occ = 8;
+        c_sms[dev] = sms;
+        c_per_sm[dev] = occ;
+        c_smem[dev] = smem;
     }
-    if (smem > 48 * 1024)
-        cudaFuncSetAttribute(train_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, train_tail_kernel, TT_THREADS, smem);
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 8) per_sm = 8;
+    const int num_sms = c_sms[dev], per_sm = c_per_sm[dev];
     int grid = num_sms * per_sm;
     if (grid > kTrainMaxGrid) grid = kTrainMaxGrid;
     const int num_tiles = p.tile_begin[KODB_NUM_LEVELS];

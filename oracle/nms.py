@@ -94,17 +94,27 @@ def candidates_for_image(x: np.ndarray, conf_thres: float, classes: Optional[Seq
     return cand.astype(np.float32), cand_row.astype(np.int64), n
 
 
-def nms_image(x: np.ndarray, conf_thres: float, nms_thres: float, classes=None) -> ImageNMS:
+def nms_image(x: np.ndarray, conf_thres: float, nms_thres: float, classes=None, backend: str = "c") -> ImageNMS:
+    """backend "c": the restated greedy kernel; "torchvision": the third-party op the reference itself
+    calls (kod/core/nms.py:69) – used by bench.py's reference arm when torchvision is importable."""
     cand, cand_row, n0 = candidates_for_image(x, conf_thres, classes)
     if cand.shape[0] == 0:
         return ImageNMS(np.zeros((0, 6), np.float32), np.zeros((0,), np.int64), cand, cand_row, n0)
     off = (cand[:, 5:6] * np.float32(MAX_WH)).astype(np.float32)
     boxes = (cand[:, :4] + off).astype(np.float32)
-    keep = greedy_nms(boxes, cand[:, 4], nms_thres)[:MAX_DET]
+    if backend == "torchvision":
+        import torch
+        import torchvision
+
+        keep = torchvision.ops.nms(torch.from_numpy(boxes), torch.from_numpy(np.ascontiguousarray(cand[:, 4])),
+                                   nms_thres).numpy()[:MAX_DET]
+    else:
+        keep = greedy_nms(boxes, cand[:, 4], nms_thres)[:MAX_DET]
     return ImageNMS(cand[keep], keep, cand, cand_row, n0)
 
 
-def non_max_suppression(detections, conf_thres: float = 0.25, nms_thres: float = 0.45, classes=None):
+def non_max_suppression(detections, conf_thres: float = 0.25, nms_thres: float = 0.45, classes=None,
+                        backend: str = "c"):
     """(B,N,5+C) -> list of ImageNMS (use `.dets` for the reference's return value)."""
     det = np.asarray(detections, dtype=np.float32)
-    return [nms_image(det[b], conf_thres, nms_thres, classes) for b in range(det.shape[0])]
+    return [nms_image(det[b], conf_thres, nms_thres, classes, backend) for b in range(det.shape[0])]
