@@ -43,9 +43,9 @@ __global__ void __launch_bounds__(DEC_TILE) decode_kernel(const __grid_constant_
                                      (float)gx, (float)gy, (float)lv.stride, lv.anchor_px[a][0], lv.anchor_px[a][1]);
         float* row = tile + tid * p.pitch;
         row[0] = bx.x; row[1] = bx.y; row[2] = bx.z; row[3] = bx.w;
-        row[4] = sigmoid_f(hd.obj[(int64_t)b * hd.obj_sb + (int64_t)a * hd.obj_sa + cell]);
+        row[4] = sigmoid_eval(hd.obj[(int64_t)b * hd.obj_sb + (int64_t)a * hd.obj_sa + cell]);
         const int64_t co = (int64_t)b * hd.cls_sb + (int64_t)a * hd.cls_sa + cell;
-        for (int j = 0; j < p.C; ++j) row[5 + j] = sigmoid_f(hd.cls[co + (int64_t)j * hd.cls_sp]);
+        for (int j = 0; j < p.C; ++j) row[5 + j] = sigmoid_eval(hd.cls[co + (int64_t)j * hd.cls_sp]);
     }
     __syncthreads();
     const int64_t row0 = (int64_t)p.row_base[L] + (int64_t)a * HW + c0;

@@ -8,30 +8,37 @@
 //                     PyCOCOMAPEvalCallback drives (pycoco_map_eval.py:50-106), on the kept detections.
 //
 // Two kernels per call:
-//  1. cand_kernel   (grid = tiles x images): one thread per anchor-cell reads obj and the C class scores
-//     once (planes are cell-contiguous -> coalesced), keeps (row, class) pairs with obj > thr and
-//     obj*cls > thr, and appends them as (score, key = row*C + class) to the image's candidate arrays.
-//     A tile's candidates are contiguous and in key order (block scan), tiles land in arbitrary order
-//     (one atomicAdd per tile); per-tile (start, count) let the reference's row-major candidate index be
-//     reconstructed for the <= 300 survivors only.  Boxes are NOT decoded here.
-//  2. select_nms_kernel (one 1024-thread CTA per image): exact top-K extraction in (score desc, key asc)
-//     order by histogram radix-select over a 64-bit composite key (robust to ties / skewed scores: bins
-//     are refined until a batch fits shared memory), bitonic sort of the batch, box decode for the batch
-//     only, greedy NMS in sub-blocks of 32 with warp-ballot suppression masks against the kept list,
-//     early exit at max_det keeps (exact: the first 300 keeps depend only on the scanned prefix).
-//     fp32 IoU arithmetic is torchvision's CPU kernel op for op (offset boxes, ratio vs DOUBLE threshold).
-//     The kept detections then go through the fp64 COCO matching while still in shared memory.
+//  1. cand_kernel (grid = tiles x images; a tile = up to 1024 contiguous cells of one (level, anchor) plane):
+//     each thread owns 4 consecutive cells and streams the obj plane and the C class planes with float4
+//     loads (issued in batches before use), keeps the (cell, class) pairs with obj > thr and obj*cls > thr
+//     (nms.py:33-48) as 16-bit ids in shared memory, then the whole CTA writes them – balanced, one pair
+//     per thread – as (score, key = row*C + class) into ONE contiguous chunk of the image's candidate
+//     arrays (one global atomicAdd per chunk).  Chunks and the entries inside a chunk land in arbitrary
+//     order: order is re-established later from the keys.  A 512-bin score histogram per image is
+//     accumulated on the side.  Boxes are NOT decoded here.
+//  2. select_nms_kernel (one 1024-thread CTA per image): exact extraction of the next-best batch in
+//     (score desc, key asc) order – cut taken from the coarse histogram; if one bin overflows the sort
+//     capacity (ties, skewed scores) it is refined by a radix-select over the 64-bit composite key –
+//     shuffle/shared-memory bitonic sort of the batch, box decode for the batch only, greedy NMS in
+//     sub-blocks of 32 with warp-ballot suppression masks against the kept list, early exit at max_det keeps
+//     (exact: the first 300 keeps depend only on the scanned prefix).  fp32 IoU arithmetic is torchvision's
+//     CPU kernel op for op (offset boxes, ratio vs DOUBLE threshold).  The reference's candidate index of
+//     each survivor (its rank among all keys of the image) is rebuilt from per-chunk counts + a count inside
+//     its own chunk.  The kept detections then go through the fp64 COCO matching while still in shared memory.
 #include "kodb_common.cuh"
 
 namespace kodb {
 
-constexpr int EV_TILE = 256;
-constexpr int NB = 4096;         // histogram bins per refinement level
-constexpr int K_CAP = 2048;      // sort capacity (batch size upper bound)
-constexpr int K_TARGET = 1024;   // preferred batch size
+constexpr int CAND_THREADS = 256;
+constexpr int CGROUP = 16;       // classes per pass of the candidate kernel
+constexpr int HB = 512;          // coarse score-histogram bins per image (32 per octave below 1.0)
+constexpr int NB = 4096;         // fine histogram bins per refinement level
+constexpr int K_CAP = 1024;      // sort capacity = one element per thread (batch size upper bound)
+constexpr int K_TARGET0 = 448;   // preferred size of the first batch; doubled for later batches
 constexpr int NMS_THREADS = 1024;
 constexpr int MAX_DET_CAP = 1024;
-constexpr int GT_CAP = 2048;     // max ground-truth boxes of ONE image in the matching stage
+constexpr int GT_CAP = 1024;     // max ground-truth boxes of ONE image in the matching stage
+constexpr int CHUNK_CAP = 4096;  // max candidate chunks (tiles x class groups) per image
 constexpr unsigned long long U64MAX = 0xffffffffffffffffull;
 
 struct EvalGeom {
@@ -46,15 +53,18 @@ struct EvalParams {
     const float* det;  // interleaved input (planar == 0)
     int64_t rows;      // rows per image
     int planar, B, C;
+    int vec;           // cells per thread in the candidate kernel (4: float4 planes, 1: generic)
+    int ngroups;       // ceil(C / CGROUP)
     kodb_nms_cfg cfg;
     // workspace
     float* cand_score;
     uint32_t* cand_key;
     int64_t cand_stride;
-    int* img_count;   // [B]   zero on entry / exit
-    int* tile_start;  // [B][tiles_per_image]
-    int* tile_count;  // [B][tiles_per_image]
-    int tiles_per_image;
+    int* img_count;    // [B]       zero on entry / exit
+    int* hist;         // [B][HB]   zero on entry / exit
+    int* chunk_start;  // [B][chunks_per_image]
+    int* chunk_count;  // [B][chunks_per_image]
+    int tiles_per_image, chunks_per_image;
     kodb_nms_out out;
     // matching
     int do_match;
@@ -63,7 +73,18 @@ struct EvalParams {
     const int32_t* gt_offsets;
     int gt_dtype;
     kodb_match_out m;
+    long long* trace;  // debug: per-image phase timestamps (clock64), NULL in production
 };
+
+#define KODB_TRACE(id)                                                                  \
+    do {                                                                                \
+        if (p.trace && tid == 0 && trace_n < 62) {                                      \
+            p.trace[(int64_t)b * 128 + 2 + 2 * trace_n] = (id);                         \
+            p.trace[(int64_t)b * 128 + 3 + 2 * trace_n] = clock64();                    \
+            ++trace_n;                                                                  \
+            p.trace[(int64_t)b * 128] = trace_n;                                        \
+        }                                                                               \
+    } while (0)
 
 // ---- score <-> sortable key ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t desc_key(float s) {
@@ -78,6 +99,19 @@ __device__ __forceinline__ float score_of_key(uint32_t k) {
 }
 __device__ __forceinline__ unsigned long long make_ck(float s, uint32_t key) {
     return ((unsigned long long)desc_key(s) << 32) | key;
+}
+// coarse bin: 0 = scores >= 1.0, then 32 bins per octave downwards; negatives / tiny scores -> HB-1
+__device__ __forceinline__ int coarse_bin(float s) {
+    const uint32_t b = __float_as_uint(s);
+    if (b >> 31) return HB - 1;
+    const int d = (int)(0x3F800000u >> 18) - (int)(b >> 18);
+    return d < 0 ? 0 : (d > HB - 1 ? HB - 1 : d);
+}
+// exclusive upper bound, in composite-key space, of coarse bins 0..d
+__device__ __forceinline__ unsigned long long coarse_hi(int d) {
+    if (d >= HB - 1) return U64MAX;
+    const uint32_t lowest_bits = ((0x3F800000u >> 18) - (uint32_t)d) << 18;  // smallest score bits inside bin d
+    return (unsigned long long)(0x80000000u - lowest_bits) << 32;
 }
 
 // ---- geometry helpers -----------------------------------------------------------------------------------
@@ -97,7 +131,7 @@ __device__ __forceinline__ void planar_row(const EvalGeom& g, int row, int& L, i
     cell = r - a * HW;
 }
 __device__ __forceinline__ int tile_of_row(const EvalParams& p, int row) {
-    if (!p.planar) return row / EV_TILE;
+    if (!p.planar) return row / CAND_THREADS;
     int L, a, cell;
     planar_row(p.g, row, L, a, cell);
     return p.g.tile_begin[L] + a * p.g.tiles_per_plane[L] + cell / p.g.tile_cells[L];
@@ -120,85 +154,120 @@ __device__ __forceinline__ float4 fetch_box(const EvalParams& p, int b, int row)
 // =========================================================================================================
 // 1. candidates
 // =========================================================================================================
-template <bool PLANAR>
-__global__ void __launch_bounds__(EV_TILE) cand_kernel(const __grid_constant__ EvalParams p) {
-    __shared__ int scan_tmp[33];
-    __shared__ int s_base;
+template <int VEC>
+struct VecLoad;
+template <>
+struct VecLoad<4> {
+    static __device__ __forceinline__ void ld(const float* p, float v[4]) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    }
+};
+template <>
+struct VecLoad<1> {
+    static __device__ __forceinline__ void ld(const float* p, float v[1]) { v[0] = __ldg(p); }
+};
+
+template <bool PLANAR, int VEC>
+__global__ void __launch_bounds__(CAND_THREADS) cand_kernel(const __grid_constant__ EvalParams p) {
+    __shared__ unsigned short s_list[CAND_THREADS * VEC * CGROUP];
+    __shared__ int s_hist[HB];
+    __shared__ int s_cnt, s_base;
     const int b = blockIdx.y, t = blockIdx.x, tid = threadIdx.x;
     const int C = p.C;
     const float thr = p.cfg.conf_thres;
     int row0, ncell;
-    const float* obj_ptr;
-    const float* cls_ptr;
-    int64_t cls_step;
+    const float* obj_base;  // address of the tile's first obj value
+    const float* cls_base;  // address of the tile's first class-0 value
+    int64_t cls_step, cell_step;
     if (PLANAR) {
         int L, a, c0;
         planar_tile(p.g, t, L, a, c0, ncell);
         const kodb_head_level& hd = p.g.head[L];
         row0 = p.g.row_base[L] + a * (p.g.lv[L].H * p.g.lv[L].W) + c0;
-        obj_ptr = hd.obj + (int64_t)b * hd.obj_sb + (int64_t)a * hd.obj_sa + c0 + tid;
-        cls_ptr = hd.cls + (int64_t)b * hd.cls_sb + (int64_t)a * hd.cls_sa + c0 + tid;
+        obj_base = hd.obj + (int64_t)b * hd.obj_sb + (int64_t)a * hd.obj_sa + c0;
+        cls_base = hd.cls + (int64_t)b * hd.cls_sb + (int64_t)a * hd.cls_sa + c0;
         cls_step = hd.cls_sp;
+        cell_step = 1;
     } else {
-        row0 = t * EV_TILE;
-        ncell = (int)min((int64_t)EV_TILE, p.rows - row0);
-        const float* r = p.det + ((int64_t)b * p.rows + row0 + tid) * (5 + C);
-        obj_ptr = r + 4;
-        cls_ptr = r + 5;
+        row0 = t * CAND_THREADS;
+        ncell = (int)min((int64_t)CAND_THREADS, p.rows - row0);
+        const float* r = p.det + ((int64_t)b * p.rows + row0) * (5 + C);
+        obj_base = r + 4;
+        cls_base = r + 5;
         cls_step = 1;
+        cell_step = 5 + C;
     }
-    float o = 0.0f;
-    bool active = false;
-    if (tid < ncell) {
-        o = PLANAR ? sigmoid_f(*obj_ptr) : *obj_ptr;
-        active = o > thr;  // nms.py:33
-    }
-    unsigned bits[KODB_MAX_CLASSES / 32] = {0u, 0u, 0u, 0u};
-    int cnt = 0;
-    if (__any_sync(KODB_FULL_MASK, active)) {
+    for (int i = tid; i < HB; i += CAND_THREADS) s_hist[i] = 0;
+    const int cell0 = tid * VEC;              // first local cell of this thread
+    const bool in_range = cell0 < ncell;      // tiles are multiples of VEC cells when VEC == 4
+    float o[VEC];
+    bool any_active = false;
+    {
+        float x[VEC];
 #pragma unroll
-        for (int w = 0; w < KODB_MAX_CLASSES / 32; ++w) {
-            const unsigned allowed = p.cfg.class_mask[w];
-            for (int jj = 0; jj < 32; ++jj) {
-                const int j = w * 32 + jj;
-                if (j >= C) break;
-                if (!((allowed >> jj) & 1u)) continue;  // `classes` filter (nms.py:54-55)
-                if (active) {
-                    const float c = PLANAR ? sigmoid_f(cls_ptr[(int64_t)j * cls_step]) : cls_ptr[(int64_t)j * cls_step];
-                    const float conf = c * o;  // nms.py:40
-                    if (conf > thr) { bits[w] |= 1u << jj; ++cnt; }
+        for (int v = 0; v < VEC; ++v) x[v] = 0.0f;
+        if (in_range) VecLoad<VEC>::ld(obj_base + (int64_t)cell0 * cell_step, x);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            o[v] = PLANAR ? sigmoid_eval(x[v]) : x[v];
+            if (!(in_range && o[v] > thr)) o[v] = -1.0f;  // nms.py:33; -1 marks "row filtered out"
+            any_active |= o[v] >= 0.0f;
+        }
+    }
+    for (int grp = 0; grp < p.ngroups; ++grp) {
+        const int j0 = grp * CGROUP, jn = min(C - j0, CGROUP);
+        if (tid == 0) s_cnt = 0;
+        __syncthreads();
+        if (any_active) {
+            const unsigned allowed = (p.cfg.class_mask[j0 >> 5] >> (j0 & 31)) & 0xffffu;  // `classes` filter (nms.py:54-55)
+            for (int jb = 0; jb < jn; jb += 4) {
+                float q[4][VEC];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (jb + u < jn) VecLoad<VEC>::ld(cls_base + (int64_t)(j0 + jb + u) * cls_step + (int64_t)cell0 * cell_step, q[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (jb + u < jn && ((allowed >> (jb + u)) & 1u)) {
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) {
+                            if (o[v] >= 0.0f) {
+                                const float c = PLANAR ? sigmoid_eval(q[u][v]) : q[u][v];
+                                if (c * o[v] > thr)  // nms.py:40, :47
+                                    s_list[atomicAdd(&s_cnt, 1)] = (unsigned short)(((cell0 + v) << 4) | (jb + u));
+                            }
+                        }
+                    }
                 }
             }
         }
-    }
-    int tot;
-    const int pos0 = block_excl_scan(cnt, scan_tmp, &tot);
-    if (tid == 0) {
-        const int base = tot ? atomicAdd(&p.img_count[b], tot) : 0;
-        s_base = base;
-        p.tile_start[(int64_t)b * p.tiles_per_image + t] = base;
-        p.tile_count[(int64_t)b * p.tiles_per_image + t] = tot;
-    }
-    __syncthreads();
-    if (cnt) {
-        float* sc = p.cand_score + (int64_t)b * p.cand_stride + s_base + pos0;
-        uint32_t* ky = p.cand_key + (int64_t)b * p.cand_stride + s_base + pos0;
-        const uint32_t kbase = (uint32_t)(row0 + tid) * (uint32_t)C;
-        int q = 0;
-#pragma unroll
-        for (int w = 0; w < KODB_MAX_CLASSES / 32; ++w) {
-            unsigned m = bits[w];
-            while (m) {
-                const int jj = __ffs(m) - 1;
-                m &= m - 1;
-                const int j = w * 32 + jj;
-                const float c = PLANAR ? sigmoid_f(cls_ptr[(int64_t)j * cls_step]) : cls_ptr[(int64_t)j * cls_step];
-                sc[q] = c * o;
-                ky[q] = kbase + j;
-                ++q;
-            }
+        __syncthreads();
+        const int n = s_cnt;
+        const int64_t chunk = (int64_t)b * p.chunks_per_image + (int64_t)t * p.ngroups + grp;
+        if (tid == 0) {
+            const int base = n ? atomicAdd(&p.img_count[b], n) : 0;
+            s_base = base;
+            p.chunk_start[chunk] = base;
+            p.chunk_count[chunk] = n;
         }
+        __syncthreads();
+        float* sc = p.cand_score + (int64_t)b * p.cand_stride + s_base;
+        uint32_t* ky = p.cand_key + (int64_t)b * p.cand_stride + s_base;
+        for (int i = tid; i < n; i += CAND_THREADS) {
+            const int pid = s_list[i];
+            const int cl = pid >> 4, j = j0 + (pid & 15);
+            const float xo = __ldg(obj_base + (int64_t)cl * cell_step);
+            const float xc = __ldg(cls_base + (int64_t)j * cls_step + (int64_t)cl * cell_step);
+            // same functions, same inputs as the filter pass -> the very same fp32 product
+            const float conf = (PLANAR ? sigmoid_eval(xc) : xc) * (PLANAR ? sigmoid_eval(xo) : xo);
+            sc[i] = conf;
+            ky[i] = (uint32_t)(row0 + cl) * (uint32_t)C + (uint32_t)j;
+            atomicAdd(&s_hist[coarse_bin(conf)], 1);
+        }
+        __syncthreads();
     }
+    for (int i = tid; i < HB; i += CAND_THREADS)
+        if (s_hist[i]) atomicAdd(&p.hist[(int64_t)b * HB + i], s_hist[i]);
 }
 
 // =========================================================================================================
@@ -206,8 +275,9 @@ __global__ void __launch_bounds__(EV_TILE) cand_kernel(const __grid_constant__ E
 // =========================================================================================================
 struct NmsSmem {
     int hist[NB];
+    int chist[HB];
+    int cprefix[CHUNK_CAP];
     unsigned long long sort_ck[K_CAP];
-    uint32_t sort_pos[K_CAP];
     float bx1[K_CAP], by1[K_CAP], bx2[K_CAP], by2[K_CAP], barea[K_CAP];
     float kx1[MAX_DET_CAP], ky1[MAX_DET_CAP], kx2[MAX_DET_CAP], ky2[MAX_DET_CAP], karea[MAX_DET_CAP];
     unsigned long long kept_ck[MAX_DET_CAP];
@@ -224,6 +294,9 @@ __device__ __forceinline__ bool suppresses(float ax1, float ay1, float ax2, floa
     // torchvision nms_kernel.cpp: fp32 throughout, ratio compared with the double threshold
     const float xx1 = fmaxf(ax1, bx1), yy1 = fmaxf(ay1, by1), xx2 = fminf(ax2, bx2), yy2 = fminf(ay2, by2);
     const float w = fmaxf(0.0f, xx2 - xx1), h = fmaxf(0.0f, yy2 - yy1);
+    // disjoint boxes (every cross-class pair, thanks to the class offset): inter == 0 -> ovr is 0 (or NaN),
+    // never > thr for thr >= 0; skip the division
+    if (thr >= 0.0 && (w == 0.0f || h == 0.0f)) return false;
     const float inter = w * h;
     const float ovr = inter / (aarea + barea - inter);
     return (double)ovr > thr;
@@ -235,6 +308,8 @@ struct MatchSmem {
     float x1[MAX_DET_CAP], y1[MAX_DET_CAP], x2[MAX_DET_CAP], y2[MAX_DET_CAP], score[MAX_DET_CAP];
     int cls[MAX_DET_CAP];
     int tp[MAX_DET_CAP];
+    double gx[GT_CAP], gy[GT_CAP], gw[GT_CAP], gh[GT_CAP];  // ground truth as [x, y, w, h] (fp64, like pycocotools)
+    int glabel[GT_CAP];
     unsigned char taken[KODB_NUM_IOU_THRS][GT_CAP];
 };
 
@@ -256,40 +331,62 @@ __device__ void match_image(MatchSmem& ms, int nk, int C, const void* gt_boxes, 
     for (int g = tid; g < ng; g += blockDim.x) {
         const long long lab = gt_labels[g0 + g];
         if (lab >= 0 && lab < C) atomicAdd(reinterpret_cast<unsigned long long*>(mo.gt_count) + lab, 1ull);
+        double l, t, r, bt;
+        load_gt_xyxy(gt_boxes, gt_dtype, g0 + g, l, t, r, bt);
+        ms.gx[g] = l; ms.gy[g] = t; ms.gw[g] = r - l; ms.gh[g] = bt - t;  // [l, t, r-l, b-t]
+        ms.glabel[g] = (int)lab;
     }
     __syncthreads();
-    // one thread per (class, threshold): sequential greedy matching in detection (score) order
-    for (int w = tid; w < C * KODB_NUM_IOU_THRS; w += blockDim.x) {
-        const int c = w / KODB_NUM_IOU_THRS, t = w - c * KODB_NUM_IOU_THRS;
-        const double thr = fmin(mo.iou_thrs[t], 1.0 - 1e-10);
-        for (int d = 0; d < nk; ++d) {
-            if (ms.cls[d] != c) continue;
-            const double dl = ms.x1[d], dt = ms.y1[d];
-            const double dw = (double)ms.x2[d] - dl, dh = (double)ms.y2[d] - dt;
-            const double da = dw * dh;
-            double best = thr;
-            int m = -1;
-            for (int g = 0; g < ng; ++g) {
-                if (gt_labels[g0 + g] != c || ms.taken[t][g]) continue;
-                double gl, gt_, gr, gb;
-                load_gt_xyxy(gt_boxes, gt_dtype, g0 + g, gl, gt_, gr, gb);
-                const double gw = gr - gl, gh = gb - gt_;
-                // maskApi.c::bbIou on [x,y,w,h]
-                const double iw = fmin(dl + dw, gl + gw) - fmax(dl, gl);
-                if (iw <= 0) { if (0.0 < best) continue; }
-                const double ih = fmin(dt + dh, gt_ + gh) - fmax(dt, gt_);
-                double iou = 0.0;
-                if (iw > 0 && ih > 0) {
-                    const double i = iw * ih;
-                    iou = i / (da + gw * gh - i);
+    // One WARP per class (no divergence between classes): lane = (GT slice 0..7) x (IoU threshold 0..3).
+    // Detections of the class are visited sequentially in score order (the greedy dependency); for each one
+    // the 8 slices scan the class's free ground truths in parallel and a shuffle reduction picks the
+    // pycocotools winner: largest IoU >= thr, ties -> the LATER ground truth.
+    const int lane = tid & 31, wid = tid >> 5, nwarps = blockDim.x >> 5;
+    const int t = lane & 3, sub = lane >> 2;
+    const double thr = fmin(mo.iou_thrs[t], 1.0 - 1e-10);
+    for (int c = wid; c < C; c += nwarps) {
+        // classes without ground truth in this image have nothing to match (all their detections are FP)
+        bool has_gt = false;
+        for (int g = lane; g < ng; g += 32) has_gt |= (ms.glabel[g] == c);
+        if (!__any_sync(KODB_FULL_MASK, has_gt)) continue;
+        for (int d0 = 0; d0 < nk; d0 += 32) {
+            const int dc = (d0 + lane < nk) ? ms.cls[d0 + lane] : -1;
+            unsigned dm = __ballot_sync(KODB_FULL_MASK, dc == c);
+            while (dm) {
+                const int d = d0 + __ffs(dm) - 1;
+                dm &= dm - 1;
+                const double dl = ms.x1[d], dt = ms.y1[d];
+                const double dw = (double)ms.x2[d] - dl, dh = (double)ms.y2[d] - dt;
+                const double da = dw * dh;
+                double best = -1.0;
+                int m = -1;
+                for (int g = sub; g < ng; g += 8) {
+                    if (ms.glabel[g] != c || ms.taken[t][g]) continue;
+                    const double gl = ms.gx[g], gt_ = ms.gy[g], gw = ms.gw[g], gh = ms.gh[g];
+                    // maskApi.c::bbIou on [x,y,w,h]
+                    const double iw = fmin(dl + dw, gl + gw) - fmax(dl, gl);
+                    const double ih = fmin(dt + dh, gt_ + gh) - fmax(dt, gt_);
+                    double iou = 0.0;
+                    if (iw > 0 && ih > 0) {
+                        const double i = iw * ih;
+                        iou = i / (da + gw * gh - i);
+                    }
+                    if (iou < thr || iou < best) continue;
+                    best = iou;  // ascending g inside a slice: a later equal IoU replaces the earlier one
+                    m = g;
                 }
-                if (iou < best) continue;
-                best = iou;
-                m = g;
-            }
-            if (m >= 0) {
-                ms.taken[t][m] = 1;
-                atomicOr(&ms.tp[d], 1 << t);
+                if (!__any_sync(KODB_FULL_MASK, m >= 0)) continue;  // no overlap >= any threshold: false positive
+#pragma unroll
+                for (int off = 4; off < 32; off <<= 1) {
+                    const double ob = __shfl_xor_sync(KODB_FULL_MASK, best, off);
+                    const int om = __shfl_xor_sync(KODB_FULL_MASK, m, off);
+                    if (ob > best || (ob == best && om > m)) { best = ob; m = om; }
+                }
+                if (m >= 0 && sub == 0) {
+                    ms.taken[t][m] = 1;
+                    atomicOr(&ms.tp[d], 1 << t);
+                }
+                __syncwarp();
             }
         }
     }
@@ -318,100 +415,140 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
     const int limit = rank_mode ? p.cfg.max_nms : n;
     const double iou_thr = p.cfg.iou_thres;
     const float max_wh = p.cfg.max_wh;
-    int* tcount = p.tile_count + (int64_t)b * p.tiles_per_image;
-    const int* tstart = p.tile_start + (int64_t)b * p.tiles_per_image;
+    const int* ccount = p.chunk_count + (int64_t)b * p.chunks_per_image;
+    const int* cstart = p.chunk_start + (int64_t)b * p.chunks_per_image;
 
+    int trace_n = 0;
+    KODB_TRACE(0);
     if (tid == 0) { s.nk = 0; }
-    // exclusive prefix of the per-tile candidate counts (tile order == row order) for index reconstruction
-    {
+    // coarse score histogram of the image (accumulated by the candidate kernel); reset for the next launch
+    for (int i = tid; i < HB; i += NMS_THREADS) {
+        s.chist[i] = p.hist[(int64_t)b * HB + i];
+        p.hist[(int64_t)b * HB + i] = 0;
+    }
+    // exclusive prefix of the per-chunk candidate counts (chunk order == key order of the tiles)
+    if (!rank_mode) {
         int carry = 0;
-        for (int t0 = 0; t0 < p.tiles_per_image; t0 += NMS_THREADS) {
+        for (int t0 = 0; t0 < p.chunks_per_image; t0 += NMS_THREADS) {
             const int t = t0 + tid;
-            const int v = t < p.tiles_per_image ? tcount[t] : 0;
+            const int v = t < p.chunks_per_image ? ccount[t] : 0;
             int tot;
             const int ex = block_excl_scan(v, s.scan_tmp, &tot);
-            if (t < p.tiles_per_image) tcount[t] = carry + ex;
+            if (t < p.chunks_per_image) s.cprefix[t] = carry + ex;
             carry += tot;
         }
     }
     __syncthreads();
+    KODB_TRACE(1);
 
-    int nk = 0, processed = 0;
-    unsigned long long lo = 0ull;
-    const unsigned long long rlo0 = (unsigned long long)desc_key(1.0f) << 32;
+    int nk = 0, processed = 0, k_target = K_TARGET0;
+    unsigned long long lo = 0ull;  // composite keys below `lo` have been consumed
+    int dnext = 0;                 // first coarse bin not consumed yet
+    bool in_fine = false;          // bin `dnext` is being consumed in pieces (it overflowed the sort capacity)
 
     while (nk < max_det && processed < limit) {
-        // ------------------------------------------------------------------ select the next batch [lo, hi)
-        unsigned long long glo = lo, ghi = U64MAX, rlo = rlo0, hi_batch = U64MAX;
-        int shift = 47, m = 0;
-        for (;;) {
-            for (int i = tid; i < NB; i += NMS_THREADS) s.hist[i] = 0;
+        unsigned long long hi_batch = U64MAX;
+        int m = 0;
+        if (!in_fine) {
+            // ------------------------------------------------------------ cut from the coarse histogram
             if (tid == 0) s.sel_bin = -1;
-            __syncthreads();
-            for (int i = tid; i < n; i += NMS_THREADS) {
-                const unsigned long long ck = make_ck(score[i], key[i]);
-                if (ck >= glo && ck < ghi) {
-                    const unsigned long long d = ck < rlo ? 0ull : ((ck - rlo) >> shift);
-                    atomicAdd(&s.hist[d > NB - 1 ? NB - 1 : (int)d], 1);
-                }
-            }
-            __syncthreads();
-            const int c0 = s.hist[4 * tid], c1 = s.hist[4 * tid + 1], c2 = s.hist[4 * tid + 2], c3 = s.hist[4 * tid + 3];
+            const int v = (tid < HB && tid >= dnext) ? s.chist[tid] : 0;
             int total;
-            const int ex = block_excl_scan(c0 + c1 + c2 + c3, s.scan_tmp, &total);
-            const int p0 = ex + c0, p1 = p0 + c1, p2 = p1 + c2, p3 = p2 + c3;
-            if (p0 >= K_TARGET && ex < K_TARGET) { s.sel_bin = 4 * tid; s.sel_p = p0; s.sel_prev = ex; }
-            else if (p1 >= K_TARGET && p0 < K_TARGET) { s.sel_bin = 4 * tid + 1; s.sel_p = p1; s.sel_prev = p0; }
-            else if (p2 >= K_TARGET && p1 < K_TARGET) { s.sel_bin = 4 * tid + 2; s.sel_p = p2; s.sel_prev = p1; }
-            else if (p3 >= K_TARGET && p2 < K_TARGET) { s.sel_bin = 4 * tid + 3; s.sel_p = p3; s.sel_prev = p2; }
+            const int ex = block_excl_scan(v, s.scan_tmp, &total);  // (barriers inside order sel_bin's reset)
+            if (ex < k_target && ex + v >= k_target) { s.sel_bin = tid; s.sel_p = ex + v; s.sel_prev = ex; }
             __syncthreads();
+            if (total == 0) break;  // nothing left
             const int d = s.sel_bin;
-            if (d < 0) { hi_batch = ghi; m = total; break; }  // fewer than K_TARGET left in range: take them all
-            const unsigned long long blo = d == 0 ? glo : max(glo, rlo + ((unsigned long long)d << shift));
-            const unsigned long long bhi = d == NB - 1 ? ghi : min(ghi, rlo + ((unsigned long long)(d + 1) << shift));
-            if (s.sel_p <= K_CAP) { hi_batch = bhi; m = s.sel_p; break; }
-            if (s.sel_prev > 0) { hi_batch = blo; m = s.sel_prev; break; }
-            // a single bin overflows the sort capacity: refine inside it
-            glo = blo; ghi = bhi; rlo = blo;
-            const unsigned long long span = ghi - glo - 1ull;
-            const int nbits = span ? 64 - __clzll((long long)span) : 0;
-            shift = nbits > 12 ? nbits - 12 : 0;
+            if (d < 0) { m = total; hi_batch = U64MAX; dnext = HB; }                     // fewer than k_target left: all
+            else if (s.sel_p <= K_CAP) { m = s.sel_p; hi_batch = coarse_hi(d); dnext = d + 1; }
+            else if (s.sel_prev > 0) { m = s.sel_prev; hi_batch = coarse_hi(d - 1); dnext = d; }
+            else { in_fine = true; dnext = d; }  // bins before d are empty; d alone overflows the sort capacity
             __syncthreads();
         }
-        if (m == 0) break;  // nothing left
-        // ------------------------------------------------------------------ collect + sort
+        if (in_fine) {
+            // ------------------------------------------------------------ radix-select inside coarse bin `dnext`
+            const unsigned long long fine_hi = coarse_hi(dnext);
+            unsigned long long glo = lo, ghi = fine_hi, rlo = lo;
+            int shift;
+            {
+                const unsigned long long span = ghi - glo - 1ull;
+                const int nbits = span ? 64 - __clzll((long long)span) : 0;
+                shift = nbits > 12 ? nbits - 12 : 0;
+            }
+            for (;;) {
+                for (int i = tid; i < NB; i += NMS_THREADS) s.hist[i] = 0;
+                if (tid == 0) s.sel_bin = -1;
+                __syncthreads();
+                for (int i = tid; i < n; i += NMS_THREADS) {
+                    const unsigned long long ck = make_ck(score[i], key[i]);
+                    if (ck >= glo && ck < ghi) {
+                        const unsigned long long d = (ck - rlo) >> shift;
+                        atomicAdd(&s.hist[d > NB - 1 ? NB - 1 : (int)d], 1);
+                    }
+                }
+                __syncthreads();
+                const int c0 = s.hist[4 * tid], c1 = s.hist[4 * tid + 1], c2 = s.hist[4 * tid + 2], c3 = s.hist[4 * tid + 3];
+                int total;
+                const int ex = block_excl_scan(c0 + c1 + c2 + c3, s.scan_tmp, &total);
+                const int p0 = ex + c0, p1 = p0 + c1, p2 = p1 + c2, p3 = p2 + c3;
+                if (p0 >= k_target && ex < k_target) { s.sel_bin = 4 * tid; s.sel_p = p0; s.sel_prev = ex; }
+                else if (p1 >= k_target && p0 < k_target) { s.sel_bin = 4 * tid + 1; s.sel_p = p1; s.sel_prev = p0; }
+                else if (p2 >= k_target && p1 < k_target) { s.sel_bin = 4 * tid + 2; s.sel_p = p2; s.sel_prev = p1; }
+                else if (p3 >= k_target && p2 < k_target) { s.sel_bin = 4 * tid + 3; s.sel_p = p3; s.sel_prev = p2; }
+                __syncthreads();
+                const int d = s.sel_bin;
+                if (d < 0) { hi_batch = ghi; m = total; break; }  // fewer than k_target left in range: take them all
+                const unsigned long long blo = d == 0 ? glo : max(glo, rlo + ((unsigned long long)d << shift));
+                const unsigned long long bhi = d == NB - 1 ? ghi : min(ghi, rlo + ((unsigned long long)(d + 1) << shift));
+                if (s.sel_p <= K_CAP) { hi_batch = bhi; m = s.sel_p; break; }
+                if (s.sel_prev > 0) { hi_batch = blo; m = s.sel_prev; break; }
+                // a single fine bin overflows too: refine inside it
+                glo = blo; ghi = bhi; rlo = blo;
+                const unsigned long long span = ghi - glo - 1ull;
+                const int nbits = span ? 64 - __clzll((long long)span) : 0;
+                shift = nbits > 12 ? nbits - 12 : 0;
+                __syncthreads();
+            }
+            if (hi_batch == fine_hi) { in_fine = false; dnext += 1; }  // the coarse bin is exhausted by this batch
+            if (m == 0) { lo = hi_batch; continue; }
+        }
+        KODB_TRACE(2);
+        // ------------------------------------------------------------------ collect [lo, hi_batch)
         if (tid == 0) s.cnt = 0;
         __syncthreads();
         for (int i = tid; i < n; i += NMS_THREADS) {
             const unsigned long long ck = make_ck(score[i], key[i]);
-            if (ck >= lo && ck < hi_batch) {
-                const int slot = atomicAdd(&s.cnt, 1);
-                s.sort_ck[slot] = ck;
-                s.sort_pos[slot] = (uint32_t)i;
-            }
+            if (ck >= lo && ck < hi_batch) s.sort_ck[atomicAdd(&s.cnt, 1)] = ck;
         }
         __syncthreads();
+        KODB_TRACE(3);
         m = s.cnt;  // == the histogram count
-        int npad = 32;
-        while (npad < m) npad <<= 1;
-        for (int i = m + tid; i < npad; i += NMS_THREADS) { s.sort_ck[i] = U64MAX; s.sort_pos[i] = 0; }
-        __syncthreads();
-        for (int k = 2; k <= npad; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int i = tid; i < npad; i += NMS_THREADS) {
-                    const int ixj = i ^ j;
-                    if (ixj > i) {
-                        const unsigned long long a = s.sort_ck[i], c = s.sort_ck[ixj];
-                        const bool up = (i & k) == 0;
-                        if ((a > c) == up) {
-                            s.sort_ck[i] = c; s.sort_ck[ixj] = a;
-                            const uint32_t pa = s.sort_pos[i]; s.sort_pos[i] = s.sort_pos[ixj]; s.sort_pos[ixj] = pa;
-                        }
+        // bitonic sort, one element per thread: compare-exchange distances < 32 stay in registers (warp
+        // shuffles), larger distances go through shared memory
+        {
+            unsigned long long myk = tid < m ? s.sort_ck[tid] : U64MAX;
+            int npad = 32;
+            while (npad < m) npad <<= 1;
+            __syncthreads();
+            for (int k = 2; k <= npad; k <<= 1) {
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    unsigned long long ok;
+                    if (j >= 32) {
+                        s.sort_ck[tid] = myk;
+                        __syncthreads();
+                        ok = s.sort_ck[tid ^ j];
+                        __syncthreads();
+                    } else {
+                        ok = __shfl_xor_sync(KODB_FULL_MASK, myk, j);
                     }
+                    const bool take_min = ((tid & j) == 0) == ((tid & k) == 0);
+                    if ((ok < myk) == take_min && ok != myk) myk = ok;
                 }
-                __syncthreads();
             }
+            s.sort_ck[tid] = myk;
+            __syncthreads();
         }
+        KODB_TRACE(4);
         int mm = m;
         if (processed + mm > limit) mm = limit - processed;  // only the top max_nms enter NMS
         // ------------------------------------------------------------------ decode the batch (offset boxes)
@@ -425,6 +562,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
             s.barea[e] = (x2 - x1) * (y2 - y1);
         }
         __syncthreads();
+        KODB_TRACE(5);
         // ------------------------------------------------------------------ greedy NMS, 32 candidates per step
         for (int s0 = 0; s0 < mm && nk < max_det; s0 += 32) {
             const int e = s0 + wid;  // warp `wid` owns candidate e
@@ -444,29 +582,25 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
             if (lane == 0) { s.alive[wid] = (e < mm) && !any; s.mask[wid] = msk; }
             __syncthreads();
             if (wid == 0) {
-                unsigned keptbits = 0u;
-                if (lane == 0) {
-                    for (int w = 0; w < 32; ++w)
-                        if (s.alive[w] && !(s.mask[w] & keptbits)) keptbits |= 1u << w;
+                // greedy resolution inside the block: kept_i = alive_i && no kept j < i suppresses i.  The
+                // triangular system is solved by fixed-point iteration with ballots (exact: its only fixed
+                // point is the greedy solution; converges in <= 32 rounds, typically 2-3)
+                const bool al = s.alive[lane] != 0;
+                const unsigned mk = s.mask[lane];
+                unsigned keptbits = __ballot_sync(KODB_FULL_MASK, al);
+                for (int it = 0; it < 33; ++it) {
+                    const unsigned nb = __ballot_sync(KODB_FULL_MASK, al && !(mk & keptbits));
+                    if (nb == keptbits) break;
+                    keptbits = nb;
                 }
-                keptbits = __shfl_sync(KODB_FULL_MASK, keptbits, 0);
                 if ((keptbits >> lane) & 1u) {
                     const int slot = nk + __popc(keptbits & ((1u << lane) - 1u));
                     if (slot < max_det) {
                         const int o = s0 + lane;
                         s.kx1[slot] = s.bx1[o]; s.ky1[slot] = s.by1[o]; s.kx2[slot] = s.bx2[o]; s.ky2[slot] = s.by2[o];
                         s.karea[slot] = s.barea[o];
-                        const unsigned long long ck = s.sort_ck[o];
-                        s.kept_ck[slot] = ck;
-                        long long idx;
-                        if (rank_mode) {
-                            idx = processed + o;
-                        } else {
-                            const uint32_t k32 = (uint32_t)ck;
-                            const int tl = tile_of_row(p, (int)(k32 / (uint32_t)C));
-                            idx = (long long)tcount[tl] + ((long long)s.sort_pos[o] - (long long)tstart[tl]);
-                        }
-                        s.kept_idx[slot] = idx;
+                        s.kept_ck[slot] = s.sort_ck[o];
+                        s.kept_idx[slot] = processed + o;  // rank in the confidence-sorted list (rank mode)
                     }
                 }
                 if (lane == 0) s.nk = min(max_det, nk + __popc(keptbits));
@@ -474,11 +608,34 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
             __syncthreads();
             nk = s.nk;
         }
+        KODB_TRACE(6);
         processed += m;
         lo = hi_batch;
+        k_target = min(2 * k_target, K_CAP / 2);
         if (hi_batch == U64MAX) break;
     }
     __syncthreads();
+
+    // ---------------------------------------------------------------------- reference candidate index
+    // nms.py:47: candidates are listed in (row, class) order, i.e. by ascending key.  index(key) = number of
+    // candidates of the image with a smaller key = [chunks of earlier tiles] + [smaller keys inside the
+    // chunks of its own tile].  One warp per survivor.
+    if (!rank_mode) {
+        for (int q = wid; q < nk; q += NMS_THREADS / 32) {
+            const uint32_t k32 = (uint32_t)s.kept_ck[q];
+            const int tl = tile_of_row(p, (int)(k32 / (uint32_t)C));
+            int cnt = 0;
+            for (int g = 0; g < p.ngroups; ++g) {
+                const int ch = tl * p.ngroups + g;
+                const uint32_t* kk = key + cstart[ch];
+                const int nc = ccount[ch];
+                for (int i = lane; i < nc; i += 32) cnt += (kk[i] < k32);
+            }
+            cnt = warp_sum_i(cnt);
+            if (lane == 0) s.kept_idx[q] = (long long)s.cprefix[tl * p.ngroups] + cnt;
+        }
+        __syncthreads();
+    }
 
     // ---------------------------------------------------------------------- outputs
     // stage the kept detections (un-offset boxes, nms.py:73) in registers, then reuse shared memory for matching
@@ -506,6 +663,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
         if (p.out.num_candidates) p.out.num_candidates[b] = n;
         p.img_count[b] = 0;  // workspace reusable without a memset
     }
+    KODB_TRACE(7);
     if (p.do_match) {
         __syncthreads();  // everyone is done with NmsSmem
         if (tid < nk) {
@@ -516,6 +674,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
         const int g0 = p.gt_offsets[b], ng = p.gt_offsets[b + 1] - g0;
         match_image(ms, nk, C, p.gt_boxes, p.gt_labels, g0, ng, p.gt_dtype, p.m, b, max_det);
     }
+    KODB_TRACE(8);
 }
 
 // standalone matching on NMS output (B, max_det, 6)
@@ -537,44 +696,64 @@ match_kernel(const float* __restrict__ dets, const int32_t* __restrict__ counts,
 }
 
 // ---------------------------------------------------------------------------------------------------------
-static int plan_geom(EvalGeom& g, const kodb_head_level* heads_h, const kodb_level_cfg* levels_h) {
+static bool aligned16e(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0; }
+
+// tile plan of the planar candidate kernel; returns tiles per image and whether float4 planes are usable
+static int plan_geom(EvalGeom& g, const kodb_head_level* heads_h, const kodb_level_cfg* levels_h, int C, int* vec_out) {
+    int vec = 4;
+    for (int l = 0; l < KODB_NUM_LEVELS; ++l) {
+        const kodb_head_level& h = heads_h[l];
+        const int HW = levels_h[l].H * levels_h[l].W;
+        if (HW <= 0 || levels_h[l].num_anchors < 1 || levels_h[l].num_anchors > KODB_MAX_ANCHORS) return -1;
+        if (HW % 4 || h.obj_sb % 4 || h.obj_sa % 4 || h.cls_sb % 4 || h.cls_sa % 4 || h.cls_sp % 4 || !aligned16e(h.obj) ||
+            !aligned16e(h.cls))
+            vec = 1;
+    }
+    (void)C;
     int rows = 0, tiles = 0;
+    const int cap = CAND_THREADS * vec;
     for (int l = 0; l < KODB_NUM_LEVELS; ++l) {
         g.head[l] = heads_h[l];
         g.lv[l] = levels_h[l];
         const int HW = levels_h[l].H * levels_h[l].W;
-        if (HW <= 0 || levels_h[l].num_anchors < 1 || levels_h[l].num_anchors > KODB_MAX_ANCHORS) return -1;
         g.row_base[l] = rows;
         rows += levels_h[l].num_anchors * HW;
-        const int tpp = (HW + EV_TILE - 1) / EV_TILE;
-        g.tiles_per_plane[l] = tpp;
-        g.tile_cells[l] = (HW + tpp - 1) / tpp;
+        const int tpp = (HW + cap - 1) / cap;
+        int tc = (HW + tpp - 1) / tpp;
+        tc = (tc + vec - 1) / vec * vec;  // multiple of the vector width (HW % 4 == 0 when vec == 4)
+        g.tiles_per_plane[l] = (HW + tc - 1) / tc;
+        g.tile_cells[l] = tc;
         g.tile_begin[l] = tiles;
-        tiles += tpp * levels_h[l].num_anchors;
+        tiles += g.tiles_per_plane[l] * levels_h[l].num_anchors;
     }
     g.row_base[KODB_NUM_LEVELS] = rows;
     g.tile_begin[KODB_NUM_LEVELS] = tiles;
+    *vec_out = vec;
     return tiles;
 }
 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-static int64_t ws_bytes(int batch, int64_t rows, int C, int tiles_per_image) {
+static int64_t ws_bytes(int batch, int64_t rows, int C, int chunks_per_image) {
     const size_t cap = (size_t)rows * C;
-    return (int64_t)(align256((size_t)batch * 4) + 2 * align256((size_t)batch * tiles_per_image * 4) +
-                     2 * align256((size_t)batch * cap * 4));
+    return (int64_t)(align256((size_t)batch * 4) + align256((size_t)batch * HB * 4) +
+                     2 * align256((size_t)batch * chunks_per_image * 4) + 2 * align256((size_t)batch * cap * 4));
 }
 
 static int carve_ws(EvalParams& p, void* ws, int64_t ws_bytes_avail) {
     const size_t cap = (size_t)p.rows * p.C;
-    if (ws_bytes_avail < ws_bytes(p.B, p.rows, p.C, p.tiles_per_image)) return KODB_ERR_CAPACITY;
+    if (ws_bytes_avail < ws_bytes(p.B, p.rows, p.C, p.chunks_per_image)) return KODB_ERR_CAPACITY;
     char* w = reinterpret_cast<char*>(ws);
+    // the two zero-on-entry arrays sit at FIXED offsets so a cached workspace survives a geometry change
+    // as long as the batch size is the same; the host layer keys its cache on the full geometry anyway
     p.img_count = reinterpret_cast<int*>(w);
     w += align256((size_t)p.B * 4);
-    p.tile_start = reinterpret_cast<int*>(w);
-    w += align256((size_t)p.B * p.tiles_per_image * 4);
-    p.tile_count = reinterpret_cast<int*>(w);
-    w += align256((size_t)p.B * p.tiles_per_image * 4);
+    p.hist = reinterpret_cast<int*>(w);
+    w += align256((size_t)p.B * HB * 4);
+    p.chunk_start = reinterpret_cast<int*>(w);
+    w += align256((size_t)p.B * p.chunks_per_image * 4);
+    p.chunk_count = reinterpret_cast<int*>(w);
+    w += align256((size_t)p.B * p.chunks_per_image * 4);
     p.cand_score = reinterpret_cast<float*>(w);
     w += align256((size_t)p.B * cap * 4);
     p.cand_key = reinterpret_cast<uint32_t*>(w);
@@ -606,7 +785,11 @@ static int setup_match(EvalParams& p, const kodb_targets* gt, const kodb_match_o
     return KODB_OK;
 }
 
-static int launch_select(const EvalParams& p, cudaStream_t st) {
+static long long* g_trace = nullptr;
+
+static int launch_select(const EvalParams& p_in, cudaStream_t st) {
+    EvalParams p = p_in;
+    p.trace = g_trace;
     const size_t smem = sizeof(NmsSmem) > sizeof(MatchSmem) ? sizeof(NmsSmem) : sizeof(MatchSmem);
     static bool attr_set[64] = {false};
     int dev = 0;
@@ -623,20 +806,24 @@ static int launch_select(const EvalParams& p, cudaStream_t st) {
 
 }  // namespace kodb
 
+// debug hook (not part of include/kodb.h): device buffer of B*128 int64 receiving per-image phase stamps
+extern "C" void kodb_debug_set_nms_trace(void* ptr) { kodb::g_trace = reinterpret_cast<long long*>(ptr); }
+
 extern "C" int64_t kodb_eval_workspace_bytes(int32_t batch, int64_t rows_per_image, int32_t num_classes) {
-    // tiles per image <= rows/1 in the worst planar case; bound it by one tile per 1 row-plane remainder:
-    // planar tiles = sum_l A*ceil(HW/256) <= rows/256 + 3*KODB_MAX_ANCHORS
-    const int tiles = (int)((rows_per_image + kodb::EV_TILE - 1) / kodb::EV_TILE) + KODB_NUM_LEVELS * KODB_MAX_ANCHORS;
-    return kodb::ws_bytes(batch, rows_per_image, num_classes, tiles);
+    // upper bound of chunks per image: tiles <= ceil(rows/256) + one ragged tile per (level, anchor) plane
+    const int tiles = (int)((rows_per_image + kodb::CAND_THREADS - 1) / kodb::CAND_THREADS) + KODB_NUM_LEVELS * KODB_MAX_ANCHORS;
+    const int groups = (num_classes + kodb::CGROUP - 1) / kodb::CGROUP;
+    return kodb::ws_bytes(batch, rows_per_image, num_classes, tiles * groups);
 }
 
 extern "C" int kodb_eval_tail(const kodb_head_level* heads_h, const kodb_level_cfg* levels_h, int32_t batch,
                               const kodb_nms_cfg* cfg_h, const kodb_nms_out* out_h, const kodb_targets* gt_h,
                               const kodb_match_out* match_h, void* workspace, int64_t workspace_bytes, void* stream) {
     using namespace kodb;
-    if (!heads_h || !levels_h || !workspace) return KODB_ERR_INVALID_ARGUMENT;
+    if (!heads_h || !levels_h || !workspace || !cfg_h) return KODB_ERR_INVALID_ARGUMENT;
     EvalParams p;
-    const int tiles = plan_geom(p.g, heads_h, levels_h);
+    int vec = 1;
+    const int tiles = plan_geom(p.g, heads_h, levels_h, cfg_h->num_classes, &vec);
     if (tiles < 0) return KODB_ERR_INVALID_ARGUMENT;
     p.det = nullptr;
     p.rows = p.g.row_base[KODB_NUM_LEVELS];
@@ -645,15 +832,21 @@ extern "C" int kodb_eval_tail(const kodb_head_level* heads_h, const kodb_level_c
     p.planar = 1;
     p.B = batch;
     p.C = cfg_h->num_classes;
+    p.vec = vec;
+    p.ngroups = (p.C + CGROUP - 1) / CGROUP;
     p.cfg = *cfg_h;
     p.out = *out_h;
     p.tiles_per_image = tiles;
+    p.chunks_per_image = tiles * p.ngroups;
+    p.trace = nullptr;
+    if (p.chunks_per_image > CHUNK_CAP) return KODB_ERR_UNSUPPORTED;
     if ((rc = carve_ws(p, workspace, workspace_bytes)) != KODB_OK) return rc;
     if ((rc = setup_match(p, gt_h, match_h)) != KODB_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int stages = cfg_h->stage_mask ? cfg_h->stage_mask : 3;
     if (stages & 1) {
-        cand_kernel<true><<<dim3(tiles, batch), EV_TILE, 0, st>>>(p);
+        if (vec == 4) cand_kernel<true, 4><<<dim3(tiles, batch), CAND_THREADS, 0, st>>>(p);
+        else cand_kernel<true, 1><<<dim3(tiles, batch), CAND_THREADS, 0, st>>>(p);
         KODB_CHECK_LAUNCH();
     }
     return (stages & 2) ? launch_select(p, st) : KODB_OK;
@@ -673,15 +866,20 @@ extern "C" int kodb_nms(const float* detections, int32_t batch, int64_t rows, co
     p.planar = 0;
     p.B = batch;
     p.C = cfg_h->num_classes;
+    p.vec = 1;
+    p.ngroups = (p.C + CGROUP - 1) / CGROUP;
     p.cfg = *cfg_h;
     p.out = *out_h;
-    p.tiles_per_image = (int)((rows + EV_TILE - 1) / EV_TILE);
+    p.tiles_per_image = (int)((rows + CAND_THREADS - 1) / CAND_THREADS);
+    p.chunks_per_image = p.tiles_per_image * p.ngroups;
+    p.trace = nullptr;
+    if (p.chunks_per_image > CHUNK_CAP) return KODB_ERR_UNSUPPORTED;
     if ((rc = carve_ws(p, workspace, workspace_bytes)) != KODB_OK) return rc;
     if ((rc = setup_match(p, gt_h, match_h)) != KODB_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int stages = cfg_h->stage_mask ? cfg_h->stage_mask : 3;
     if (stages & 1) {
-        cand_kernel<false><<<dim3(p.tiles_per_image, batch), EV_TILE, 0, st>>>(p);
+        cand_kernel<false, 1><<<dim3(p.tiles_per_image, batch), CAND_THREADS, 0, st>>>(p);
         KODB_CHECK_LAUNCH();
     }
     return (stages & 2) ? launch_select(p, st) : KODB_OK;

@@ -33,6 +33,47 @@ __device__ __forceinline__ float softplus_sigmoid(float x, float* sig) {
     return fmaxf(x, 0.0f) + log1pf(e);
 }
 
+// ---- streaming-rate math for the dense passes -----------------------------------------------------------
+// The dense kernels touch every head logit once; the libm-accurate expf/log1pf/IEEE-division chain
+// (~100 instructions per logit) made them issue-bound.  These versions cost ~10-30 instructions and stay
+// within ~3 ulp: exp via ex2.approx with the rounding error of x*log2(e) compensated (2 FMAs), reciprocal
+// via the correctly-rounded __frcp_rn, log1p on [0,1] via a degree-9 polynomial (max rel. error 1.7e-7).
+__device__ __forceinline__ float ex2_approx(float y) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y));
+    return r;
+}
+__device__ __forceinline__ float exp_fast(float x) {  // |x| <= 87 (callers clamp)
+    const float L2E = 1.44269502162933349609375f, L2E_LO = 1.92596299e-8f;
+    const float y = x * L2E;
+    float r = fmaf(x, L2E, -y);  // exact residual of the rounded product
+    r = fmaf(x, L2E_LO, r);
+    const float e = ex2_approx(y);
+    return fmaf(e, r * 0.693147182464599609375f, e);
+}
+// eval-side sigmoid (decode + candidate filter share it, so the fused path and get_detections agree bit for bit)
+__device__ __forceinline__ float sigmoid_eval(float x) {
+    const float t = fminf(fmaxf(-x, -87.0f), 87.0f);
+    return __frcp_rn(1.0f + exp_fast(t));
+}
+// softplus(x) and sigmoid(x) for the dense objectness pass
+__device__ __forceinline__ float softplus_sigmoid_fast(float x, float* sig) {
+    const float e = exp_fast(-fminf(fabsf(x), 87.0f));  // (0, 1]
+    const float inv = __frcp_rn(1.0f + e);
+    *sig = x >= 0.0f ? inv : e * inv;
+    float q = -0.003256378462538123f;
+    q = fmaf(q, e, 0.019907161593437195f);
+    q = fmaf(q, e, -0.057064201682806015f);
+    q = fmaf(q, e, 0.10614264756441116f);
+    q = fmaf(q, e, -0.15311862528324127f);
+    q = fmaf(q, e, 0.19678117334842682f);
+    q = fmaf(q, e, -0.24954558908939362f);
+    q = fmaf(q, e, 0.33330005407333374f);
+    q = fmaf(q, e, -0.4999990463256836f);
+    q = fmaf(q, e, 1.0f);
+    return fmaf(q, e, fmaxf(x, 0.0f));  // max(x,0) + log1p(e)
+}
+
 // torch.remainder(x, 1) for floats: fmod then shift negatives by +1 (ATen remainder kernel).
 __device__ __forceinline__ float remainder_one(float x) {
     float r = fmodf(x, 1.0f);
@@ -106,9 +147,9 @@ __device__ __forceinline__ long long clamp_ll(long long v, long long lo, long lo
 // ---- eval decode of one anchor-cell (layers.py:55-63 + torchvision _box_cxcywh_to_xyxy) ----------
 __device__ __forceinline__ float4 decode_box(float p0, float p1, float p2, float p3, float gx, float gy, float stride,
                                              float aw_px, float ah_px) {
-    float cx = ((sigmoid_f(p0) * 2.0f + gx) - 0.5f) * stride;
-    float cy = ((sigmoid_f(p1) * 2.0f + gy) - 0.5f) * stride;
-    float sw = sigmoid_f(p2) * 2.0f, sh = sigmoid_f(p3) * 2.0f;
+    float cx = ((sigmoid_eval(p0) * 2.0f + gx) - 0.5f) * stride;
+    float cy = ((sigmoid_eval(p1) * 2.0f + gy) - 0.5f) * stride;
+    float sw = sigmoid_eval(p2) * 2.0f, sh = sigmoid_eval(p3) * 2.0f;
     float w = (sw * sw) * aw_px;
     float h = (sh * sh) * ah_px;
     float hw = 0.5f * w, hh = 0.5f * h;

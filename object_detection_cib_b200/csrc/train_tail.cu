@@ -1,24 +1,36 @@
 // kodb_train_tail — Yolov5Loss.forward (kod/lightning/experiments/yv5_baseline/loss.py:166-248) fused
 // with its backward and with the target assignment it starts from (yv5.py:207-296).
 //
-// One persistent kernel.  The nine gradient tensors are cut into tiles = (level, image, anchor, <=256
-// contiguous cells of the H*W plane) x all 5+C channels.  A CTA owns a tile completely:
-//   1. it re-derives, from the image's ground-truth list, the assigned rows that fall into the tile
-//      (order-preserving compaction, key = (offset, target) = the reference's row order for a fixed anchor);
-//   2. per row: gathers 4 box + 1 obj logits from their planes, IoU-family forward + analytic backward
-//      (iou.py:77-246), objectness target t = clamp(iou, 0) (NOT detached, loss.py:109-118);
-//   3. streams the tile: reads the obj logits once (softplus / sigmoid -> BCE sum and dobj) and
-//      zero-fills the 4 + C box/cls gradient planes (the dense dY the 1x1 head convs consume);
-//   4. after a barrier, patches the assigned cells: summed duplicate gradients, last-writer-wins
-//      objectness target (index_put_ semantics), class BCE with pos_weight (loss.py:155-160).
-// Loss partials are reduced in fp64 per CTA and finalised by the last CTA in a fixed order
-// (deterministic).  No host sync, no data-dependent shapes; N_l is recomputed per CTA from the targets.
+// ONE launch with two kinds of CTAs (CTA-level specialisation):
+//
+//  * dense CTAs (blockIdx < dense_grid) — pure HBM streaming over the nine gradient tensors (the dense dY
+//    the 1x1 head convs consume): read every objectness logit ONCE (float4), write
+//    dobj = s*sigmoid(x) (the BCE gradient for target 0) and accumulate softplus(x) (the BCE value for
+//    target 0); zero-fill the dbox / dcls planes.  Grid-stride float4 loops over contiguous planar
+//    tensors, streaming stores, no dependence on the targets.  They carry ~all algorithmic bytes,
+//    4*AC*(1+5+C) per image.  When done, each publishes its fp64 partial and bumps a completion counter.
+//
+//  * sparse CTAs (one per (image, level), scheduled after the dense ones) — re-derive the level's assigned
+//    rows of the image from its ground-truth list (order-preserving compaction: for a fixed anchor the
+//    reference's row order is (offset, target)), gather 4 box + 1 obj + C cls logits per row, run the
+//    IoU-family forward + analytic backward (iou.py:77-246).  All of that overlaps the dense stream.
+//    Only then do they wait for the dense completion counter (dense CTAs never wait on anybody and are
+//    scheduled first, so the spin cannot deadlock) and patch the assigned cells on top of the dense
+//    output: summed duplicate gradients, last-writer-wins objectness target (index_put_ semantics,
+//    SURVEY A.3; the target is NOT detached, loss.py:109-118), class BCE with pos_weight
+//    (loss.py:155-160).  N_l (needed by every gradient scale) is recomputed per CTA from the flat target
+//    list.  The last sparse CTA reduces all fp64 partials in a fixed order -> deterministic losses.
+//
+// No host sync, no data-dependent shapes, CUDA-graph capturable.
+#include <stdlib.h>
+
 #include "kodb_common.cuh"
 
 namespace kodb {
 
-constexpr int TT_THREADS = 256;
-constexpr int TT_TILE = 256;  // max cells per tile
+constexpr int TD_THREADS = 256;
+constexpr int TS_THREADS = 256;
+constexpr int TD_MAX_GRID = 148 * 8;
 
 struct TrainParams {
     kodb_head_level head[KODB_NUM_LEVELS];
@@ -37,13 +49,163 @@ struct TrainParams {
     int skip_if_equal, has_grads;
     float* losses;
     int32_t* n_assigned;
-    int tiles_per_plane[KODB_NUM_LEVELS], tile_cells[KODB_NUM_LEVELS], tile_begin[KODB_NUM_LEVELS + 1];
-    int vec_ok[KODB_NUM_LEVELS];
-    int row_cap;  // shared-memory row capacity (>= 5 * max targets per image)
-    double* partials;       // [gridDim.x][9]
-    unsigned int* counter;  // zero on entry, zero on exit
+    int contiguous[KODB_NUM_LEVELS];  // planar tensors of the level are flat arrays (fast path)
+    int row_cap;                      // shared-memory row capacity of the sparse CTAs
+    int cls_in_smem;                  // class-BCE gradients of the rows fit in shared memory
+    int dense_grid;
+    double* dense_partials;   // [TD_MAX_GRID][3]   softplus sums per level
+    double* sparse_partials;  // [B*3][3]           (loc, obj correction, cls) per (image, level)
+    unsigned int* counter;    // zero on entry, zero on exit
+    int* nl_pub;              // [3] N_l published by the b == 0 CTAs for the finaliser
+    unsigned int* dense_done; // completion counter of the dense CTAs; zero on entry / exit
+    long long* trace;         // debug: per-CTA phase stamps (globaltimer ns), NULL in production
 };
 
+__device__ __forceinline__ long long gtime() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define TT_TRACE(slot)                                                                    \
+    do {                                                                                  \
+        if (p.trace && threadIdx.x == 0) p.trace[(int64_t)blockIdx.x * 8 + (slot)] = gtime(); \
+    } while (0)
+
+__device__ __forceinline__ bool load_upstream(const TrainParams& p, float up[3]) {
+    if (p.up_dev) {
+        up[0] = p.up_dev[0]; up[1] = p.up_dev[1]; up[2] = p.up_dev[2];
+        if (p.skip_if_equal && up[0] == p.up_h[0] && up[1] == p.up_h[1] && up[2] == p.up_h[2]) return false;
+    } else {
+        up[0] = p.up_h[0]; up[1] = p.up_h[1]; up[2] = p.up_h[2];
+    }
+    return true;
+}
+
+__device__ __forceinline__ double block_sum_d(double v, double* sm /* >= 32 */) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r += sm[i];  // fixed order
+    return r;
+}
+
+__device__ __forceinline__ void st_zero4(float* p) {
+    // streaming store: the gradients are consumed by a later kernel, not re-read here
+    __stcs(reinterpret_cast<float4*>(p), make_float4(0.f, 0.f, 0.f, 0.f));
+}
+
+// =========================================================================================================
+// 1. dense stream
+// =========================================================================================================
+__device__ __forceinline__ void zero_flat(float* ptr, int64_t n, int64_t gtid, int64_t gsize) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = gtid; i < n4; i += gsize) st_zero4(ptr + 4 * i);
+    for (int64_t i = (n4 << 2) + gtid; i < n; i += gsize) ptr[i] = 0.0f;
+}
+
+// generic (strided) addressing of element i of a logical (B, A, P, HW) tensor
+__device__ __forceinline__ int64_t strided_off(int64_t i, int HW, int P, int A, int64_t sb, int64_t sa, int64_t sp) {
+    const int cell = (int)(i % HW);
+    int64_t r = i / HW;
+    const int pl = (int)(r % P);
+    r /= P;
+    const int a = (int)(r % A);
+    const int64_t b = r / A;
+    return b * sb + a * sa + (int64_t)pl * sp + cell;
+}
+
+__device__ __forceinline__ void dense_cta(const TrainParams& p, const float up[3], double* red_tmp, int* cnt_tmp) {
+    TT_TRACE(0);
+    // N_l = number of assigned rows per level over the whole batch: the first B dense CTAs count one image
+    // each (a handful of targets) and accumulate with integer atomics; the sparse CTAs read the totals after
+    // the dense-completion wait, so no extra barrier is needed.
+    for (int img = blockIdx.x; img < p.B; img += p.dense_grid) {
+        if (threadIdx.x < KODB_NUM_LEVELS) cnt_tmp[threadIdx.x] = 0;
+        __syncthreads();
+        const int t0 = p.img_offsets[img], Tb = p.img_offsets[img + 1] - t0;
+        for (int i = threadIdx.x; i < Tb * KODB_NUM_LEVELS; i += TD_THREADS) {
+            const int n = t0 + i / KODB_NUM_LEVELS, l = i % KODB_NUM_LEVELS;
+            const kodb_level_cfg& lv = p.lv[l];
+            GtRow g = load_gt_row(p.boxes, p.boxes_dtype, p.labels, n, 1.0 / (double)lv.stride);
+            const int nb = __popc(neighbour_bits(g.cx, g.cy, lv.fm_w, lv.fm_h));
+            int c = 0;
+            for (int k = 0; k < lv.num_anchors; ++k)
+                if (anchor_keeps(g.w, g.h, lv.anchor_grid[k][0], lv.anchor_grid[k][1], p.thr)) c += nb;
+            if (c) atomicAdd(&cnt_tmp[l], c);
+        }
+        __syncthreads();
+        if (threadIdx.x < KODB_NUM_LEVELS && cnt_tmp[threadIdx.x]) atomicAdd(&p.nl_pub[threadIdx.x], cnt_tmp[threadIdx.x]);
+        __syncthreads();
+    }
+    const int64_t gtid = (int64_t)blockIdx.x * TD_THREADS + threadIdx.x;
+    const int64_t gsize = (int64_t)p.dense_grid * TD_THREADS;
+    double acc[KODB_NUM_LEVELS];
+#pragma unroll
+    for (int L = 0; L < KODB_NUM_LEVELS; ++L) {
+        const kodb_level_cfg& lv = p.lv[L];
+        const kodb_head_level& hd = p.head[L];
+        const kodb_grad_level& gd = p.grad[L];
+        const int HW = lv.H * lv.W, A = lv.num_anchors;
+        const int64_t n_obj = (int64_t)p.B * A * HW;
+        const float s_obj = (float)((double)up[1] * p.lam_obj * (double)lv.obj_ratio / (double)n_obj);
+        float a0 = 0.0f;
+        if (p.contiguous[L]) {
+            // objectness: read once, BCE(x, 0) value + gradient
+            const int64_t n4 = n_obj >> 2;
+            for (int64_t i = gtid; i < n4; i += gsize) {
+                const float4 x = __ldcs(reinterpret_cast<const float4*>(hd.obj) + i);
+                float4 g;
+                float s0, s1, s2, s3;
+                const float v0 = softplus_sigmoid_fast(x.x, &s0), v1 = softplus_sigmoid_fast(x.y, &s1);
+                const float v2 = softplus_sigmoid_fast(x.z, &s2), v3 = softplus_sigmoid_fast(x.w, &s3);
+                a0 += (v0 + v1) + (v2 + v3);
+                if (p.has_grads) {
+                    g.x = s_obj * s0; g.y = s_obj * s1; g.z = s_obj * s2; g.w = s_obj * s3;
+                    __stcs(reinterpret_cast<float4*>(gd.obj) + i, g);
+                }
+            }
+            for (int64_t i = (n4 << 2) + gtid; i < n_obj; i += gsize) {
+                float sg;
+                a0 += softplus_sigmoid_fast(hd.obj[i], &sg);
+                if (p.has_grads) gd.obj[i] = s_obj * sg;
+            }
+            if (p.has_grads) {
+                zero_flat(gd.box, n_obj * 4, gtid, gsize);
+                zero_flat(gd.cls, n_obj * p.C, gtid, gsize);
+            }
+        } else {
+            for (int64_t i = gtid; i < n_obj; i += gsize) {
+                float sg;
+                a0 += softplus_sigmoid_fast(hd.obj[strided_off(i, HW, 1, A, hd.obj_sb, hd.obj_sa, 0)], &sg);
+                if (p.has_grads) gd.obj[strided_off(i, HW, 1, A, gd.obj_sb, gd.obj_sa, 0)] = s_obj * sg;
+            }
+            if (p.has_grads) {
+                for (int64_t i = gtid; i < n_obj * 4; i += gsize)
+                    gd.box[strided_off(i, HW, 4, A, gd.box_sb, gd.box_sa, gd.box_sp)] = 0.0f;
+                for (int64_t i = gtid; i < n_obj * p.C; i += gsize)
+                    gd.cls[strided_off(i, HW, p.C, A, gd.cls_sb, gd.cls_sa, gd.cls_sp)] = 0.0f;
+            }
+        }
+        acc[L] = (double)a0;
+    }
+#pragma unroll
+    for (int L = 0; L < KODB_NUM_LEVELS; ++L) {
+        const double s = block_sum_d(acc[L], red_tmp);
+        if (threadIdx.x == 0) p.dense_partials[(size_t)blockIdx.x * 3 + L] = s;
+    }
+    __syncthreads();  // every thread's stores are issued
+    if (threadIdx.x == 0) {
+        __threadfence();  // release: stores of this CTA visible device-wide before the counter moves
+        atomicAdd(p.dense_done, 1u);
+    }
+    TT_TRACE(1);
+}
+
+// =========================================================================================================
+// 2. sparse rows
+// =========================================================================================================
 __device__ __forceinline__ float w_gt(float a, float b) { return a > b ? 1.0f : (a == b ? 0.5f : 0.0f); }
 __device__ __forceinline__ float w_lt(float a, float b) { return a < b ? 1.0f : (a == b ? 0.5f : 0.0f); }
 __device__ __forceinline__ float sgn(float a) { return a > 0.0f ? 1.0f : (a < 0.0f ? -1.0f : 0.0f); }
@@ -144,295 +306,270 @@ __device__ __forceinline__ float iou_metric(int type, float eps, const float p[4
     return val;
 }
 
-__device__ __forceinline__ void tile_decode(const TrainParams& p, int t, int& L, int& b, int& a, int& c0, int& ncell) {
-    L = t >= p.tile_begin[2] ? 2 : (t >= p.tile_begin[1] ? 1 : 0);
-    int r = t - p.tile_begin[L];
-    const int tpp = p.tiles_per_plane[L];
-    const int chunk = r % tpp;
-    r /= tpp;
-    const int A = p.lv[L].num_anchors;
-    a = r % A;
-    b = r / A;
-    const int HW = p.lv[L].H * p.lv[L].W;
-    c0 = chunk * p.tile_cells[L];
-    ncell = min(p.tile_cells[L], HW - c0);
-}
 
-__device__ __forceinline__ double block_sum_d(double v, double* sm /* >= 8 */) {
-    v = warp_sum(v);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double r = 0.0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r += sm[i];  // fixed order
+// shared-memory row record of the sparse CTAs (structure of arrays, capacity p.row_cap)
+struct SparseRows {
+    int* id;       // anchor * HW + cell
+    int* label;
+    float* val;    // IoU-family metric of the row
+    float* xo;     // objectness logit at the cell
+    float4* d;     // d(metric)/d(box logits), unscaled
+    int* flags;    // bit0: first row of its cell ("leader"), bit1: last row of its cell (index_put_ winner)
+    int* next;     // next row with the same cell (-1: none): the duplicate chain, in reference row order
+    float* gcls;   // [row_cap * C] unscaled class-BCE gradient per (row, class) when cls_in_smem
+};
+
+__device__ __forceinline__ SparseRows carve_rows(unsigned char* smem_raw, int cap) {
+    SparseRows r;
+    r.d = reinterpret_cast<float4*>(smem_raw);
+    r.id = reinterpret_cast<int*>(r.d + cap);
+    r.label = r.id + cap;
+    r.val = reinterpret_cast<float*>(r.label + cap);
+    r.xo = r.val + cap;
+    r.flags = reinterpret_cast<int*>(r.xo + cap);
+    r.next = r.flags + cap;
+    r.gcls = reinterpret_cast<float*>(r.next + cap);
     return r;
 }
 
-__global__ void __launch_bounds__(TT_THREADS) train_tail_kernel(const __grid_constant__ TrainParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int scan_tmp[33];
-    __shared__ double red_tmp[TT_THREADS / 32];
-    __shared__ int s_NL[KODB_NUM_LEVELS];
-    __shared__ int s_last;
-
+__device__ __forceinline__ void sparse_cta(const TrainParams& p, const float up[3], unsigned char* smem_raw,
+                                           int* scan_tmp, double* red_tmp, int& s_last) {
     const int tid = threadIdx.x;
-    float up[3];
-    if (p.up_dev) {
-        up[0] = p.up_dev[0]; up[1] = p.up_dev[1]; up[2] = p.up_dev[2];
-        if (p.skip_if_equal && up[0] == p.up_h[0] && up[1] == p.up_h[1] && up[2] == p.up_h[2]) return;
-    } else {
-        up[0] = p.up_h[0]; up[1] = p.up_h[1]; up[2] = p.up_h[2];
-    }
+    const int sid = blockIdx.x - p.dense_grid;
+    const int b = sid / KODB_NUM_LEVELS, L = sid - b * KODB_NUM_LEVELS;
+    TT_TRACE(0);
 
-    // shared row records (SoA), capacity row_cap
-    int* r_cell = reinterpret_cast<int*>(smem_raw);
-    int* r_label = r_cell + p.row_cap;
-    float* r_t = reinterpret_cast<float*>(r_label + p.row_cap);
-    float* r_x = r_t + p.row_cap;                               // obj logit at the cell
-    float4* r_g = reinterpret_cast<float4*>(r_x + p.row_cap);   // combined d/d(box logits)
+    const kodb_level_cfg& lv = p.lv[L];
+    const kodb_head_level& hd = p.head[L];
+    const kodb_grad_level& gd = p.grad[L];
+    const int W = lv.W, H = lv.H, HW = H * W, A = lv.num_anchors, C = p.C;
+    const double inv_stride = 1.0 / (double)lv.stride;
+    const SparseRows R_ = carve_rows(smem_raw, p.row_cap);
 
-    // ---- N_l: number of assigned rows per level (needed up-front: every gradient is scaled by 1/N_l) ----
-    {
-        int cnt[KODB_NUM_LEVELS] = {0, 0, 0};
-        for (int n = tid; n < p.T; n += TT_THREADS) {
+    double acc_loc = 0.0, acc_obj = 0.0, acc_cls = 0.0;
+
+    // ---- rows of (image b, level L): index i = (k*5 + o)*Tb + n, i.e. (offset, target) order per anchor ----
+    const int t0 = p.img_offsets[b], Tb = p.img_offsets[b + 1] - t0;
+    const int total = 5 * A * Tb;
+    int R = 0;
+    for (int start = 0; start < total; start += TS_THREADS) {
+        const int i = start + tid;
+        int flag = 0, cell = 0, k = 0;
+        GtRow g;
+        float gxf = 0.f, gyf = 0.f;
+        if (i < total) {
+            const int ko = i / Tb, n = t0 + (i - ko * Tb);
+            k = ko / 5;
+            const int o = ko - k * 5;
+            g = load_gt_row(p.boxes, p.boxes_dtype, p.labels, n, inv_stride);
+            if (anchor_keeps(g.w, g.h, lv.anchor_grid[k][0], lv.anchor_grid[k][1], p.thr) &&
+                ((neighbour_bits(g.cx, g.cy, lv.fm_w, lv.fm_h) >> o) & 1u)) {
+                const long long gi = trunc_ll(g.cx - offset_x(o)), gj = trunc_ll(g.cy - offset_y(o));
+                cell = (int)(clamp_ll(gj, 0, H - 1) * W + clamp_ll(gi, 0, W - 1));
+                flag = 1;
+                gxf = g.cx - (float)gi;  // the gt box uses the UNclamped cell (yv5.py:281)
+                gyf = g.cy - (float)gj;
+            }
+        }
+        int tot;
+        const int pos = R + block_excl_scan(flag, scan_tmp, &tot);
+        if (flag) {
+            const float aw = lv.anchor_grid[k][0], ah = lv.anchor_grid[k][1];
+            const int64_t bo = (int64_t)b * hd.box_sb + (int64_t)k * hd.box_sa + cell;
+            float pl[4];
 #pragma unroll
-            for (int L = 0; L < KODB_NUM_LEVELS; ++L) {
-                const kodb_level_cfg& lv = p.lv[L];
-                GtRow g = load_gt_row(p.boxes, p.boxes_dtype, p.labels, n, 1.0 / (double)lv.stride);
-                int nb = __popc(neighbour_bits(g.cx, g.cy, lv.fm_w, lv.fm_h));
-                for (int k = 0; k < lv.num_anchors; ++k)
-                    if (anchor_keeps(g.w, g.h, lv.anchor_grid[k][0], lv.anchor_grid[k][1], p.thr)) cnt[L] += nb;
-            }
+            for (int q = 0; q < 4; ++q) pl[q] = hd.box[bo + q * hd.box_sp];
+            const float xo = hd.obj[(int64_t)b * hd.obj_sb + (int64_t)k * hd.obj_sa + cell];
+            float d[4];
+            const float val = iou_metric(p.iou_type, p.eps, pl, aw, ah, gxf, gyf, g.w, g.h, d);
+            acc_loc += (double)(1.0f - val);
+            R_.id[pos] = k * HW + cell;
+            R_.label[pos] = g.label;
+            R_.val[pos] = val;
+            R_.xo[pos] = xo;
+            R_.d[pos] = make_float4(d[0], d[1], d[2], d[3]);
         }
-#pragma unroll
-        for (int L = 0; L < KODB_NUM_LEVELS; ++L) {
-            int w = warp_sum_i(cnt[L]);
-            __syncthreads();
-            if ((tid & 31) == 0) scan_tmp[tid >> 5] = w;
-            __syncthreads();
-            if (tid == 0) {
-                int s = 0;
-                for (int i = 0; i < TT_THREADS / 32; ++i) s += scan_tmp[i];
-                s_NL[L] = s;
-            }
-        }
-        __syncthreads();
-        if (blockIdx.x == 0 && tid < KODB_NUM_LEVELS && p.n_assigned) p.n_assigned[tid] = s_NL[tid];
-    }
-
-    double acc_loc[KODB_NUM_LEVELS] = {0, 0, 0}, acc_obj[KODB_NUM_LEVELS] = {0, 0, 0}, acc_cls[KODB_NUM_LEVELS] = {0, 0, 0};
-    const int C = p.C;
-    const int num_tiles = p.tile_begin[KODB_NUM_LEVELS];
-
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        int L, b, a, c0, ncell;
-        tile_decode(p, t, L, b, a, c0, ncell);
-        const kodb_level_cfg& lv = p.lv[L];
-        const kodb_head_level& hd = p.head[L];
-        const kodb_grad_level& gd = p.grad[L];
-        const int W = lv.W, H = lv.H;
-        const int NL = s_NL[L];
-        const double n_obj = (double)p.B * lv.num_anchors * H * W;
-        const float s_loc = (float)((double)up[0] * p.lam_loc / (double)NL);
-        const float s_obj = (float)((double)up[1] * p.lam_obj * (double)lv.obj_ratio / n_obj);
-        const float s_cls = (float)((double)up[2] * p.lam_cls / ((double)NL * (double)C));
-        const float aw = lv.anchor_grid[a][0], ah = lv.anchor_grid[a][1];
-        const double inv_stride = 1.0 / (double)lv.stride;
-
-        // ---- 1. rows of this tile, in (offset, target) order ----------------------------------------
-        const int t0 = p.img_offsets[b], Tb = p.img_offsets[b + 1] - t0;
-        int R = 0;
-        for (int start = 0; start < 5 * Tb; start += TT_THREADS) {
-            const int i = start + tid;
-            int flag = 0, cell = 0;
-            GtRow g;
-            float gxf = 0.f, gyf = 0.f;
-            if (i < 5 * Tb) {
-                const int o = i / Tb, n = t0 + (i - o * Tb);
-                g = load_gt_row(p.boxes, p.boxes_dtype, p.labels, n, inv_stride);
-                if (anchor_keeps(g.w, g.h, aw, ah, p.thr) && ((neighbour_bits(g.cx, g.cy, lv.fm_w, lv.fm_h) >> o) & 1u)) {
-                    const long long gi = trunc_ll(g.cx - offset_x(o)), gj = trunc_ll(g.cy - offset_y(o));
-                    cell = (int)(clamp_ll(gj, 0, H - 1) * W + clamp_ll(gi, 0, W - 1));
-                    flag = (cell >= c0 && cell < c0 + ncell);
-                    gxf = g.cx - (float)gi;  // gt box uses the UNclamped cell (yv5.py:281)
-                    gyf = g.cy - (float)gj;
-                }
-            }
-            int tot;
-            const int pos = R + block_excl_scan(flag, scan_tmp, &tot);
-            if (flag) {
-                // ---- 2. per-row IoU forward/backward ------------------------------------------------
-                const int64_t bo = (int64_t)b * hd.box_sb + (int64_t)a * hd.box_sa + cell;
-                float pl[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) pl[q] = hd.box[bo + q * hd.box_sp];
-                const float xo = hd.obj[(int64_t)b * hd.obj_sb + (int64_t)a * hd.obj_sa + cell];
-                float d[4];
-                const float val = iou_metric(p.iou_type, p.eps, pl, aw, ah, gxf, gyf, g.w, g.h, d);
-                acc_loc[L] += (double)(1.0f - val);
-                // dL/d(val): localisation mean(1 - val) and the non-detached objectness target
-                const float gv = -s_loc + (val >= 0.0f ? -xo * s_obj : 0.0f);
-                r_cell[pos] = cell;
-                r_label[pos] = g.label;
-                r_t[pos] = fmaxf(val, 0.0f);
-                r_x[pos] = xo;
-                r_g[pos] = make_float4(gv * d[0], gv * d[1], gv * d[2], gv * d[3]);
-            }
-            R += tot;
-        }
-
-        // ---- 3. dense stream of the tile -------------------------------------------------------------
-        if (tid < ncell) {
-            const int64_t oo = (int64_t)b * hd.obj_sb + (int64_t)a * hd.obj_sa + c0 + tid;
-            float sig;
-            const float sp = softplus_sigmoid(hd.obj[oo], &sig);
-            acc_obj[L] += (double)sp;
-            if (p.has_grads) gd.obj[(int64_t)b * gd.obj_sb + (int64_t)a * gd.obj_sa + c0 + tid] = s_obj * sig;
-        }
-        if (p.has_grads) {
-            const int planes = 4 + C;
-            if (p.vec_ok[L]) {
-                const int nv = ncell >> 2;
-                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int idx = tid; idx < planes * nv; idx += TT_THREADS) {
-                    const int pl = idx / nv, v = idx - pl * nv;
-                    float* base = pl < 4 ? gd.box + (int64_t)b * gd.box_sb + (int64_t)a * gd.box_sa + (int64_t)pl * gd.box_sp
-                                         : gd.cls + (int64_t)b * gd.cls_sb + (int64_t)a * gd.cls_sa + (int64_t)(pl - 4) * gd.cls_sp;
-                    reinterpret_cast<float4*>(base + c0)[v] = z;
-                }
-            } else {
-                for (int idx = tid; idx < planes * ncell; idx += TT_THREADS) {
-                    const int pl = idx / ncell, v = idx - pl * ncell;
-                    float* base = pl < 4 ? gd.box + (int64_t)b * gd.box_sb + (int64_t)a * gd.box_sa + (int64_t)pl * gd.box_sp
-                                         : gd.cls + (int64_t)b * gd.cls_sb + (int64_t)a * gd.cls_sa + (int64_t)(pl - 4) * gd.cls_sp;
-                    base[c0 + v] = 0.0f;
-                }
-            }
-        }
-
-        // ---- 4. patch the assigned cells --------------------------------------------------------------
-        if (R > 0) {
-            __syncthreads();  // rows visible; tile's dense stores ordered before the patches
-            // box + objectness: one thread per row
-            for (int r = tid; r < R; r += TT_THREADS) {
-                const int cell = r_cell[r];
-                bool leader = true, last = true;
-                for (int q = 0; q < r; ++q) leader &= (r_cell[q] != cell);
-                for (int q = r + 1; q < R; ++q) last &= (r_cell[q] != cell);
-                if (last) {
-                    // index_put_ last-writer-wins target (loss.py:113-118): BCE(x,t) = softplus(x) - t*x
-                    acc_obj[L] -= (double)(r_t[r] * r_x[r]);
-                    if (p.has_grads) {
-                        const float sig = sigmoid_f(r_x[r]);
-                        gd.obj[(int64_t)b * gd.obj_sb + (int64_t)a * gd.obj_sa + cell] = s_obj * (sig - r_t[r]);
-                    }
-                }
-                if (leader && p.has_grads) {
-                    float4 s = r_g[r];
-                    for (int q = r + 1; q < R; ++q)
-                        if (r_cell[q] == cell) { const float4 o4 = r_g[q]; s.x += o4.x; s.y += o4.y; s.z += o4.z; s.w += o4.w; }
-                    float* gb = gd.box + (int64_t)b * gd.box_sb + (int64_t)a * gd.box_sa + cell;
-                    gb[0] = s.x; gb[gd.box_sp] = s.y; gb[2 * gd.box_sp] = s.z; gb[3 * gd.box_sp] = s.w;
-                }
-            }
-            // classification: one thread per (row, class)
-            for (int idx = tid; idx < R * C; idx += TT_THREADS) {
-                const int r = idx / C, c = idx - r * C;
-                const int cell = r_cell[r];
-                const float q = hd.cls[(int64_t)b * hd.cls_sb + (int64_t)a * hd.cls_sa + (int64_t)c * hd.cls_sp + cell];
-                float sig;
-                const float spn = softplus_sigmoid(-q, &sig);  // -log sigmoid(q); sig = sigmoid(-q) = 1 - sigmoid(q)
-                const float pw = p.pos_weight ? p.pos_weight[c] : 1.0f;
-                const float tgt = (r_label[r] == c) ? 1.0f : 0.0f;
-                const float lw = 1.0f + (pw - 1.0f) * tgt;
-                acc_cls[L] += (double)((1.0f - tgt) * q + lw * spn);
-                if (p.has_grads) {
-                    bool leader = true;
-                    for (int k = 0; k < r; ++k) leader &= (r_cell[k] != cell);
-                    if (leader) {
-                        float s = ((1.0f - tgt) - lw * sig) * s_cls;
-                        for (int k = r + 1; k < R; ++k)
-                            if (r_cell[k] == cell) {
-                                const float t2 = (r_label[k] == c) ? 1.0f : 0.0f;
-                                const float lw2 = 1.0f + (pw - 1.0f) * t2;
-                                s += ((1.0f - t2) - lw2 * sig) * s_cls;
-                            }
-                        gd.cls[(int64_t)b * gd.cls_sb + (int64_t)a * gd.cls_sa + (int64_t)c * gd.cls_sp + cell] = s;
-                    }
-                }
-            }
-            __syncthreads();  // rows are overwritten by the next tile
-        }
-    }
-
-    // ---- loss partials -> workspace; the last CTA finalises in a fixed order ---------------------------
-    double part[9];
-#pragma unroll
-    for (int L = 0; L < KODB_NUM_LEVELS; ++L) {
-        part[L] = block_sum_d(acc_loc[L], red_tmp);
-        part[3 + L] = block_sum_d(acc_obj[L], red_tmp);
-        part[6 + L] = block_sum_d(acc_cls[L], red_tmp);
-    }
-    if (tid == 0) {
-#pragma unroll
-        for (int i = 0; i < 9; ++i) p.partials[(size_t)blockIdx.x * 9 + i] = part[i];
-        __threadfence();
-        const unsigned prev = atomicAdd(p.counter, 1u);
-        s_last = (prev == gridDim.x - 1);
+        R += tot;
     }
     __syncthreads();
+    // duplicate structure: leader / last flags and the chain to the next row of the same cell
+    for (int r = tid; r < R; r += TS_THREADS) {
+        const int id = R_.id[r];
+        int fl = 3, nx = -1;
+        for (int q = 0; q < r; ++q)
+            if (R_.id[q] == id) { fl &= ~1; break; }
+        for (int q = r + 1; q < R; ++q)
+            if (R_.id[q] == id) { fl &= ~2; nx = q; break; }
+        R_.flags[r] = fl;
+        R_.next[r] = nx;
+        if (fl & 2) acc_obj -= (double)(fmaxf(R_.val[r], 0.0f) * R_.xo[r]);  // BCE(x,t) = softplus(x) - t*x, last writer
+    }
+    // classification: one thread per (row, class); value now, gradient kept unscaled in shared memory
+    for (int idx = tid; idx < R * C; idx += TS_THREADS) {
+        const int r = idx / C, c = idx - r * C;
+        const int id = R_.id[r];
+        const int k = id / HW, cell = id - k * HW;
+        const float q = hd.cls[(int64_t)b * hd.cls_sb + (int64_t)k * hd.cls_sa + (int64_t)c * hd.cls_sp + cell];
+        float sig;
+        const float spn = softplus_sigmoid(-q, &sig);  // -log sigmoid(q); sig = 1 - sigmoid(q)
+        const float pw = p.pos_weight ? p.pos_weight[c] : 1.0f;
+        const float tgt = (R_.label[r] == c) ? 1.0f : 0.0f;
+        const float lw = 1.0f + (pw - 1.0f) * tgt;
+        acc_cls += (double)((1.0f - tgt) * q + lw * spn);
+        if (p.cls_in_smem) R_.gcls[idx] = (1.0f - tgt) - lw * sig;
+    }
+    TT_TRACE(2);
+
+    // ---- wait for the dense stream: everything above overlapped it; the patches below must land on top ----
+    if (tid == 0) {
+        while (atomicAdd(p.dense_done, 0u) < (unsigned)p.dense_grid) __nanosleep(100);
+        __threadfence();  // acquire (also orders the N_l counters the dense CTAs accumulated)
+    }
+    __syncthreads();
+    TT_TRACE(3);
+    const int NL = (int)__ldcg(&p.nl_pub[L]);
+    const double n_obj = (double)p.B * A * H * W;
+    const float s_loc = (float)((double)up[0] * p.lam_loc / (double)NL);
+    const float s_obj = (float)((double)up[1] * p.lam_obj * (double)lv.obj_ratio / n_obj);
+    const float s_cls = (float)((double)up[2] * p.lam_cls / ((double)NL * (double)C));
+
+    // ---- patch the assigned cells (the dense CTAs have written s*sigmoid / zeros) ------------------------
+    if (p.has_grads) {
+        for (int r = tid; r < R; r += TS_THREADS) {
+            const int id = R_.id[r], fl = R_.flags[r];
+            const int k = id / HW, cell = id - k * HW;
+            if (fl & 2)  // index_put_ last-writer-wins target (loss.py:113-118)
+                gd.obj[(int64_t)b * gd.obj_sb + (int64_t)k * gd.obj_sa + cell] =
+                    s_obj * (sigmoid_f(R_.xo[r]) - fmaxf(R_.val[r], 0.0f));
+            if (fl & 1) {
+                float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int q = r; q >= 0; q = R_.next[q]) {  // every duplicate receives (and contributes) gradient
+                    const float v = R_.val[q];
+                    // dL/d(val): localisation mean(1 - val) and the non-detached objectness target
+                    const float gv = -s_loc + (v >= 0.0f ? -R_.xo[q] * s_obj : 0.0f);
+                    const float4 d4 = R_.d[q];
+                    s.x += gv * d4.x; s.y += gv * d4.y; s.z += gv * d4.z; s.w += gv * d4.w;
+                }
+                float* gb = gd.box + (int64_t)b * gd.box_sb + (int64_t)k * gd.box_sa + cell;
+                gb[0] = s.x; gb[gd.box_sp] = s.y; gb[2 * gd.box_sp] = s.z; gb[3 * gd.box_sp] = s.w;
+            }
+        }
+        for (int idx = tid; idx < R * C; idx += TS_THREADS) {
+            const int r = idx / C, c = idx - r * C;
+            if (!(R_.flags[r] & 1)) continue;
+            const int id = R_.id[r];
+            const int k = id / HW, cell = id - k * HW;
+            float s = 0.0f;
+            if (p.cls_in_smem) {
+                for (int q = r; q >= 0; q = R_.next[q]) s += R_.gcls[q * C + c] * s_cls;
+            } else {  // row list too large for shared-memory gradients: recompute from the logit
+                const float qv = hd.cls[(int64_t)b * hd.cls_sb + (int64_t)k * hd.cls_sa + (int64_t)c * hd.cls_sp + cell];
+                float sig;
+                softplus_sigmoid(-qv, &sig);
+                const float pw = p.pos_weight ? p.pos_weight[c] : 1.0f;
+                for (int q = r; q >= 0; q = R_.next[q]) {
+                    const float tgt = (R_.label[q] == c) ? 1.0f : 0.0f;
+                    const float lw = 1.0f + (pw - 1.0f) * tgt;
+                    s += ((1.0f - tgt) - lw * sig) * s_cls;
+                }
+            }
+            gd.cls[(int64_t)b * gd.cls_sb + (int64_t)k * gd.cls_sa + (int64_t)c * gd.cls_sp + cell] = s;
+        }
+    }
+    TT_TRACE(4);
+
+    // ---- partials -> workspace; the last CTA finalises in a fixed order -----------------------------------
+    const double pl_ = block_sum_d(acc_loc, red_tmp);
+    const double po_ = block_sum_d(acc_obj, red_tmp);
+    const double pc_ = block_sum_d(acc_cls, red_tmp);
+    const unsigned nblocks = gridDim.x - p.dense_grid;
+    if (tid == 0) {
+        double* dst = p.sparse_partials + ((size_t)b * KODB_NUM_LEVELS + L) * 3;
+        dst[0] = pl_; dst[1] = po_; dst[2] = pc_;
+        __threadfence();
+        const unsigned prev = atomicAdd(p.counter, 1u);
+        s_last = (prev == nblocks - 1);
+    }
+    __syncthreads();
+    TT_TRACE(5);
     if (!s_last) return;
     __threadfence();
-    double tot[9];
+    // all loads first (independent, L2), then ONE block reduction of the nine sums in a fixed order
+    double v[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) {
-        double v = 0.0;
-        for (int c = tid; c < (int)gridDim.x; c += TT_THREADS) v += __ldcg(&p.partials[(size_t)c * 9 + i]);
-        tot[i] = block_sum_d(v, red_tmp);
+    for (int i = 0; i < 9; ++i) v[i] = 0.0;
+    for (int i = tid; i < p.B * KODB_NUM_LEVELS; i += TS_THREADS) {
+        const int l = i % KODB_NUM_LEVELS;
+        const double* src = p.sparse_partials + (size_t)i * 3;
+        const double a0 = __ldcg(src), a1 = __ldcg(src + 1), a2 = __ldcg(src + 2);
+#pragma unroll
+        for (int q = 0; q < KODB_NUM_LEVELS; ++q)
+            if (q == l) { v[q] += a0; v[3 + q] += a1; v[6 + q] += a2; }
     }
+    for (int i = tid; i < p.dense_grid; i += TS_THREADS) {
+        const double* src = p.dense_partials + (size_t)i * 3;
+        v[3] += __ldcg(src); v[4] += __ldcg(src + 1); v[5] += __ldcg(src + 2);
+    }
+    double* red9 = reinterpret_cast<double*>(smem_raw);  // rows are dead; >= 8 warps * 9 doubles available
+#pragma unroll
+    for (int i = 0; i < 9; ++i) v[i] = warp_sum(v[i]);
+    __syncthreads();
+    if ((tid & 31) == 0) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) red9[(tid >> 5) * 9 + i] = v[i];
+    }
+    __syncthreads();
     if (tid == 0) {
+        double tot[9];
+        for (int i = 0; i < 9; ++i) {
+            double s = 0.0;
+            for (int w = 0; w < TS_THREADS / 32; ++w) s += red9[w * 9 + i];
+            tot[i] = s;
+        }
         double loc = 0.0, obj = 0.0, cls = 0.0;
-        for (int L = 0; L < KODB_NUM_LEVELS; ++L) {
-            const kodb_level_cfg& lv = p.lv[L];
-            const double n_obj = (double)p.B * lv.num_anchors * lv.H * lv.W;
-            const double nl = (double)s_NL[L];
-            loc += tot[L] / nl;  // 0/0 -> NaN: mean over an empty level (loss.py:96)
-            obj += (double)lv.obj_ratio * (tot[3 + L] / n_obj);
-            cls += tot[6 + L] / (nl * (double)C);
+        for (int l = 0; l < KODB_NUM_LEVELS; ++l) {
+            const kodb_level_cfg& q = p.lv[l];
+            const int nl = __ldcg(&p.nl_pub[l]);
+            const double nobj = (double)p.B * q.num_anchors * q.H * q.W;
+            loc += tot[l] / (double)nl;  // 0/0 -> NaN: mean over an empty level (loss.py:96)
+            obj += (double)q.obj_ratio * (tot[3 + l] / nobj);
+            cls += tot[6 + l] / ((double)nl * (double)C);
+            if (p.n_assigned) p.n_assigned[l] = nl;
         }
         p.losses[0] = (float)(p.lam_loc * loc);
         p.losses[1] = (float)(p.lam_obj * obj);
         p.losses[2] = (float)(p.lam_cls * cls);
         *p.counter = 0u;
+        *p.dense_done = 0u;
+        p.nl_pub[0] = 0; p.nl_pub[1] = 0; p.nl_pub[2] = 0;
     }
+    TT_TRACE(6);
 }
 
-static int plan_tiles(TrainParams& p) {
-    int begin = 0;
-    for (int l = 0; l < KODB_NUM_LEVELS; ++l) {
-        const int HW = p.lv[l].H * p.lv[l].W;
-        if (HW <= 0) return KODB_ERR_INVALID_ARGUMENT;
-        const int tpp = (HW + TT_TILE - 1) / TT_TILE;
-        int tc = (HW + tpp - 1) / tpp;
-        tc = (tc + 3) & ~3;
-        if (tc > TT_TILE) tc = TT_TILE;
-        p.tiles_per_plane[l] = (HW + tc - 1) / tc;
-        p.tile_cells[l] = tc;
-        p.tile_begin[l] = begin;
-        begin += p.tiles_per_plane[l] * p.lv[l].num_anchors * p.B;
-    }
-    p.tile_begin[KODB_NUM_LEVELS] = begin;
-    return KODB_OK;
+__global__ void __launch_bounds__(TS_THREADS, 4) train_tail_kernel(const __grid_constant__ TrainParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int scan_tmp[33];
+    __shared__ double red_tmp[32];
+    __shared__ int s_last;
+    float up[3];
+    if (!load_upstream(p, up)) return;
+    if ((int)blockIdx.x < p.dense_grid) dense_cta(p, up, red_tmp, scan_tmp);
+    else sparse_cta(p, up, smem_raw, scan_tmp, red_tmp, s_last);
 }
 
+static long long* g_tt_trace = nullptr;
 static bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0; }
 
 }  // namespace kodb
 
-static const int kTrainMaxGrid = 148 * 8;
+// debug hook (not part of include/kodb.h): device buffer of (grid)*8 int64 phase stamps per CTA
+extern "C" void kodb_debug_set_train_trace(void* ptr) { kodb::g_tt_trace = reinterpret_cast<long long*>(ptr); }
 
-extern "C" int64_t kodb_train_workspace_bytes(int32_t, int32_t) {
-    return (int64_t)kTrainMaxGrid * 9 * sizeof(double) + 256;
+static size_t tt_align(size_t v) { return (v + 255) & ~(size_t)255; }
+
+extern "C" int64_t kodb_train_workspace_bytes(int32_t batch, int32_t) {
+    return (int64_t)(tt_align((size_t)kodb::TD_MAX_GRID * 3 * sizeof(double)) +
+                     tt_align((size_t)(batch > 0 ? batch : 1) * 9 * sizeof(double)) + 256);
 }
 
 extern "C" int kodb_train_tail(const kodb_head_level* heads_h, const kodb_level_cfg* levels_h,
@@ -445,13 +582,16 @@ extern "C" int kodb_train_tail(const kodb_head_level* heads_h, const kodb_level_
     if (workspace_bytes < kodb_train_workspace_bytes(t->batch, t->max_per_image)) return KODB_ERR_CAPACITY;
     if (cfg->num_classes < 1 || cfg->num_classes > KODB_MAX_CLASSES) return KODB_ERR_INVALID_ARGUMENT;
     if (cfg->iou_type < KODB_IOU_IOU || cfg->iou_type > KODB_IOU_CIOU) return KODB_ERR_INVALID_ARGUMENT;
-    if (t->batch < 1 || t->num_targets < 0 || t->max_per_image < 0) return KODB_ERR_INVALID_ARGUMENT;
+    if (t->batch < 1 || t->batch > 65535 || t->num_targets < 0 || t->max_per_image < 0) return KODB_ERR_INVALID_ARGUMENT;
     TrainParams p;
+    int amax = 1;
     for (int l = 0; l < KODB_NUM_LEVELS; ++l) {
         if (levels_h[l].num_anchors < 1 || levels_h[l].num_anchors > KODB_MAX_ANCHORS) return KODB_ERR_INVALID_ARGUMENT;
+        if (levels_h[l].H < 1 || levels_h[l].W < 1) return KODB_ERR_INVALID_ARGUMENT;
         p.head[l] = heads_h[l];
         p.lv[l] = levels_h[l];
         if (grads_h) p.grad[l] = grads_h[l]; else p.grad[l] = kodb_grad_level{};
+        if (levels_h[l].num_anchors > amax) amax = levels_h[l].num_anchors;
     }
     p.boxes = t->boxes;
     p.labels = t->labels;
@@ -474,53 +614,66 @@ extern "C" int kodb_train_tail(const kodb_head_level* heads_h, const kodb_level_
     p.has_grads = grads_h != nullptr;
     p.losses = losses;
     p.n_assigned = n_assigned;
-    int rc = plan_tiles(p);
-    if (rc != KODB_OK) return rc;
     for (int l = 0; l < KODB_NUM_LEVELS; ++l) {
-        const int HW = p.lv[l].H * p.lv[l].W;
-        bool ok = (HW % 4 == 0) && p.has_grads;
-        if (ok) {
+        const int64_t HW = (int64_t)p.lv[l].H * p.lv[l].W;
+        const int A = p.lv[l].num_anchors;
+        const kodb_head_level& h = p.head[l];
+        bool ok = h.obj_sa == HW && h.obj_sb == A * HW && aligned16(h.obj);
+        if (ok && p.has_grads) {
             const kodb_grad_level& g = p.grad[l];
-            ok = aligned16(g.box) && aligned16(g.cls) && g.box_sb % 4 == 0 && g.box_sa % 4 == 0 && g.box_sp % 4 == 0 &&
-                 g.cls_sb % 4 == 0 && g.cls_sa % 4 == 0 && g.cls_sp % 4 == 0;
+            ok = g.obj_sa == HW && g.obj_sb == A * HW && g.box_sp == HW && g.box_sa == 4 * HW && g.box_sb == 4 * A * HW &&
+                 g.cls_sp == HW && g.cls_sa == (int64_t)p.C * HW && g.cls_sb == (int64_t)p.C * A * HW && aligned16(g.obj) &&
+                 aligned16(g.box) && aligned16(g.cls);
         }
-        p.vec_ok[l] = ok ? 1 : 0;
+        p.contiguous[l] = ok ? 1 : 0;
     }
-    p.row_cap = 5 * (t->max_per_image > 0 ? t->max_per_image : 1);
-    const size_t smem = (size_t)p.row_cap * (4 * sizeof(int) + sizeof(float4));
-    if (smem > 200 * 1024) return KODB_ERR_CAPACITY;  // > ~5000 boxes in ONE image
-    p.partials = reinterpret_cast<double*>(workspace);
-    p.counter = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(workspace) + (size_t)kTrainMaxGrid * 9 * sizeof(double));
+    p.row_cap = 5 * amax * (t->max_per_image > 0 ? t->max_per_image : 1);
+    size_t smem = (size_t)p.row_cap * (6 * sizeof(int) + sizeof(float4));
+    if (smem > 160 * 1024) return KODB_ERR_CAPACITY;  // > ~270 boxes in ONE image (reference data has <= ~72)
+    const size_t cls_bytes = (size_t)p.row_cap * p.C * sizeof(float);
+    p.cls_in_smem = (smem + cls_bytes <= 96 * 1024) ? 1 : 0;
+    if (p.cls_in_smem) smem += cls_bytes;
+    if (smem < 8 * 9 * sizeof(double)) smem = 8 * 9 * sizeof(double);  // the finaliser's reduction scratch
+    // fixed offsets first (counter / N_l), so a cached workspace stays valid when the batch size changes
+    char* w = reinterpret_cast<char*>(workspace);
+    p.counter = reinterpret_cast<unsigned int*>(w);
+    p.nl_pub = reinterpret_cast<int*>(w + 64);
+    p.dense_done = reinterpret_cast<unsigned int*>(w + 128);
+    w += 256;
+    p.dense_partials = reinterpret_cast<double*>(w);
+    w += tt_align((size_t)TD_MAX_GRID * 3 * sizeof(double));
+    p.sparse_partials = reinterpret_cast<double*>(w);
 
-    // launch geometry is cached per device (no attribute / occupancy queries on the steady-state path,
-    // which also keeps the call capturable into a CUDA graph after one warm-up launch)
-    static int c_sms[64] = {0}, c_per_sm[64] = {0};
+    // launch geometry cached per device (keeps the call capturable into a CUDA graph after one warm-up)
+    static int c_sms[64] = {0};
     static size_t c_smem[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) return KODB_ERR_UNSUPPORTED;
-    if (c_sms[dev] == 0 || c_smem[dev] != smem) {
+    if (c_sms[dev] == 0) {
         int sms = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-        if (smem > 48 * 1024 &&
-            cudaFuncSetAttribute(train_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        c_sms[dev] = sms > 0 ? sms : 148;
+    }
+    if (smem > 48 * 1024 && c_smem[dev] < smem) {
+        if (cudaFuncSetAttribute(train_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return KODB_ERR_LAUNCH;
-        int occ = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, train_tail_kernel, TT_THREADS, smem);
-        if (occ < 1) occ = 1;
-        if (occ > 8) occ = 8;
-        c_sms[dev] = sms;
-        c_per_sm[dev] = occ;
         c_smem[dev] = smem;
     }
-    const int num_sms = c_sms[dev], per_sm = c_per_sm[dev];
-    int grid = num_sms * per_sm;
-    if (grid > kTrainMaxGrid) grid = kTrainMaxGrid;
-    const int num_tiles = p.tile_begin[KODB_NUM_LEVELS];
-    if (grid > num_tiles) grid = num_tiles;
-    if (grid < 1) grid = 1;
-    train_tail_kernel<<<grid, TT_THREADS, smem, (cudaStream_t)stream>>>(p);
+    // dense CTAs first (lowest block ids are scheduled first and never wait), then one sparse CTA per
+    // (image, level).  Three dense CTAs per SM leave room for the sparse ones to run concurrently.
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        const char* e = getenv("KODB_TRAIN_DENSE_PER_SM");  // tuning knob; default chosen on B200
+        per_sm = e ? atoi(e) : 3;
+        if (per_sm < 1 || per_sm > 8) per_sm = 3;
+    }
+    int grid_dense = c_sms[dev] * per_sm;
+    if (grid_dense > TD_MAX_GRID) grid_dense = TD_MAX_GRID;
+    p.dense_grid = grid_dense;
+    p.trace = g_tt_trace;
+    cudaStream_t st = (cudaStream_t)stream;
+    train_tail_kernel<<<grid_dense + p.B * KODB_NUM_LEVELS, TS_THREADS, smem, st>>>(p);
     KODB_CHECK_LAUNCH();
     return KODB_OK;
 }
