@@ -36,6 +36,7 @@ constexpr int NB = 4096;         // fine histogram bins per refinement level
 constexpr int K_CAP = 1024;      // sort capacity = one element per thread (batch size upper bound)
 constexpr int K_TARGET0 = 448;   // preferred size of the first batch; doubled for later batches
 constexpr int NMS_THREADS = 1024;
+constexpr int NMS_STEP = 128;     // candidates resolved per NMS step (4 per warp)
 constexpr int MAX_DET_CAP = 1024;
 constexpr int GT_CAP = 1024;     // max ground-truth boxes of ONE image in the matching stage
 constexpr int CHUNK_CAP = 4096;  // max candidate chunks (tiles x class groups) per image
@@ -171,6 +172,7 @@ struct VecLoad<1> {
 template <bool PLANAR, int VEC>
 __global__ void __launch_bounds__(CAND_THREADS) cand_kernel(const __grid_constant__ EvalParams p) {
     __shared__ unsigned short s_list[CAND_THREADS * VEC * CGROUP];
+    __shared__ float s_o[CAND_THREADS * VEC];  // sigmoid(obj) of the tile's cells (exact values for pass 2)
     __shared__ int s_hist[HB];
     __shared__ int s_cnt, s_base;
     const int b = blockIdx.y, t = blockIdx.x, tid = threadIdx.x;
@@ -199,9 +201,13 @@ __global__ void __launch_bounds__(CAND_THREADS) cand_kernel(const __grid_constan
         cell_step = 5 + C;
     }
     for (int i = tid; i < HB; i += CAND_THREADS) s_hist[i] = 0;
-    const int cell0 = tid * VEC;              // first local cell of this thread
-    const bool in_range = cell0 < ncell;      // tiles are multiples of VEC cells when VEC == 4
-    float o[VEC];
+    const int cell0 = tid * VEC;          // first local cell of this thread
+    const bool in_range = cell0 < ncell;  // tiles are multiples of VEC cells when VEC == 4
+    // Per cell: the objectness o (row filter, nms.py:33) and -- for the planar input -- the class-LOGIT window
+    // around  logit(thr / o):  sigmoid(q) * o > thr  <=>  q > logit(thr / o)  in exact arithmetic.  Logits
+    // outside the +-2e-3 window are decided by one comparison; only the (rare) ones inside pay for the exact
+    // fp32 product, so the decision is always the one the decode kernel's arithmetic would give.
+    float o[VEC], t_lo[VEC], t_hi[VEC];
     bool any_active = false;
     {
         float x[VEC];
@@ -210,15 +216,34 @@ __global__ void __launch_bounds__(CAND_THREADS) cand_kernel(const __grid_constan
         if (in_range) VecLoad<VEC>::ld(obj_base + (int64_t)cell0 * cell_step, x);
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-            o[v] = PLANAR ? sigmoid_eval(x[v]) : x[v];
-            if (!(in_range && o[v] > thr)) o[v] = -1.0f;  // nms.py:33; -1 marks "row filtered out"
-            any_active |= o[v] >= 0.0f;
+            const float ov = PLANAR ? sigmoid_eval(x[v]) : x[v];
+            const bool act = in_range && ov > thr;
+            o[v] = act ? ov : -1.0f;  // -1 marks "row filtered out"
+            if (in_range) s_o[cell0 + v] = ov;
+            any_active |= act;
+            if (PLANAR) {
+                float lo_ = 3.0e38f, hi_ = 3.0e38f;  // inactive cell: nothing passes
+                if (act && thr > 0.0f) {
+                    const float r = __fdividef(thr, ov);  // in (0, 1)
+                    const float tau = __logf(__fdividef(r, 1.0f - r));
+                    lo_ = tau - 2.0e-3f;
+                    hi_ = tau + 2.0e-3f;
+                    if (!(r < 0.99f)) { lo_ = -3.0e38f; hi_ = 3.0e38f; }  // ill-conditioned near r -> 1: exact test
+                } else if (act) {  // thr <= 0: every class of an active row goes to the exact test
+                    lo_ = -3.0e38f;
+                    hi_ = 3.0e38f;
+                }
+                t_lo[v] = lo_;
+                t_hi[v] = hi_;
+            }
         }
     }
     for (int grp = 0; grp < p.ngroups; ++grp) {
         const int j0 = grp * CGROUP, jn = min(C - j0, CGROUP);
         if (tid == 0) s_cnt = 0;
         __syncthreads();
+        // flagged (class, cell) pairs of this thread: bit (class_in_group * VEC + v)
+        unsigned long long bits = 0ull;
         if (any_active) {
             const unsigned allowed = (p.cfg.class_mask[j0 >> 5] >> (j0 & 31)) & 0xffffu;  // `classes` filter (nms.py:54-55)
             for (int jb = 0; jb < jn; jb += 4) {
@@ -226,19 +251,40 @@ __global__ void __launch_bounds__(CAND_THREADS) cand_kernel(const __grid_constan
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
                     if (jb + u < jn) VecLoad<VEC>::ld(cls_base + (int64_t)(j0 + jb + u) * cls_step + (int64_t)cell0 * cell_step, q[u]);
+                unsigned m16 = 0u;  // bit (u * VEC + v), compile-time positions
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    if (jb + u < jn && ((allowed >> (jb + u)) & 1u)) {
+                    if (jb + u < jn) {
 #pragma unroll
                         for (int v = 0; v < VEC; ++v) {
-                            if (o[v] >= 0.0f) {
-                                const float c = PLANAR ? sigmoid_eval(q[u][v]) : q[u][v];
-                                if (c * o[v] > thr)  // nms.py:40, :47
-                                    s_list[atomicAdd(&s_cnt, 1)] = (unsigned short)(((cell0 + v) << 4) | (jb + u));
+                            if (PLANAR) {
+                                // inactive cells carry t_lo = +inf, so one comparison rejects ~90% of the pairs
+                                if (q[u][v] > t_lo[v] && ((q[u][v] > t_hi[v]) || (sigmoid_eval(q[u][v]) * o[v] > thr)))
+                                    m16 |= 1u << (u * VEC + v);
+                            } else {
+                                if (o[v] >= 0.0f && (q[u][v] * o[v] > thr)) m16 |= 1u << (u * VEC + v);  // nms.py:40, :47
                             }
                         }
                     }
                 }
+                if (allowed != 0xffffu) {  // rare: the `classes` argument was given
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (!((allowed >> (jb + u)) & 1u)) m16 &= ~(((1u << VEC) - 1u) << (u * VEC));
+                }
+                bits |= (unsigned long long)m16 << (jb * VEC);
+            }
+        }
+        int slot = 0;
+        const int mine = __popcll(bits);
+        if (mine) slot = atomicAdd(&s_cnt, mine);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            unsigned w32 = half ? (unsigned)(bits >> 32) : (unsigned)bits;
+            while (w32) {
+                const int bi = __ffs(w32) - 1 + 32 * half;
+                w32 &= w32 - 1;
+                s_list[slot++] = (unsigned short)(((cell0 + (bi % VEC)) << 4) | (bi / VEC));
             }
         }
         __syncthreads();
@@ -256,10 +302,9 @@ __global__ void __launch_bounds__(CAND_THREADS) cand_kernel(const __grid_constan
         for (int i = tid; i < n; i += CAND_THREADS) {
             const int pid = s_list[i];
             const int cl = pid >> 4, j = j0 + (pid & 15);
-            const float xo = __ldg(obj_base + (int64_t)cl * cell_step);
             const float xc = __ldg(cls_base + (int64_t)j * cls_step + (int64_t)cl * cell_step);
-            // same functions, same inputs as the filter pass -> the very same fp32 product
-            const float conf = (PLANAR ? sigmoid_eval(xc) : xc) * (PLANAR ? sigmoid_eval(xo) : xo);
+            // the decode kernel's arithmetic: sigmoid_eval(cls) * sigmoid_eval(obj)
+            const float conf = (PLANAR ? sigmoid_eval(xc) : xc) * s_o[cl];
             sc[i] = conf;
             ky[i] = (uint32_t)(row0 + cl) * (uint32_t)C + (uint32_t)j;
             atomicAdd(&s_hist[coarse_bin(conf)], 1);
@@ -283,8 +328,8 @@ struct NmsSmem {
     unsigned long long kept_ck[MAX_DET_CAP];
     long long kept_idx[MAX_DET_CAP];
     int scan_tmp[33];
-    int alive[32];
-    unsigned mask[32];
+    int alive[NMS_STEP];
+    unsigned mask[NMS_STEP][NMS_STEP / 32];
     int sel_bin, sel_p, sel_prev;
     int cnt, nk;
 };
@@ -308,10 +353,18 @@ struct MatchSmem {
     float x1[MAX_DET_CAP], y1[MAX_DET_CAP], x2[MAX_DET_CAP], y2[MAX_DET_CAP], score[MAX_DET_CAP];
     int cls[MAX_DET_CAP];
     int tp[MAX_DET_CAP];
-    double gx[GT_CAP], gy[GT_CAP], gw[GT_CAP], gh[GT_CAP];  // ground truth as [x, y, w, h] (fp64, like pycocotools)
+    unsigned long long gmask[MAX_DET_CAP];  // ground truths (< 64) of the detection's class overlapping it at all
+};
+// ground truth of the image, staged once at kernel start (its own region: it must survive the NMS phase)
+struct GtSmem {
+    double gx[GT_CAP], gy[GT_CAP], gw[GT_CAP], gh[GT_CAP];  // [x, y, w, h] in fp64, like pycocotools
     int glabel[GT_CAP];
     unsigned char taken[KODB_NUM_IOU_THRS][GT_CAP];
 };
+
+constexpr size_t kNmsRegion =
+    ((sizeof(NmsSmem) > sizeof(MatchSmem) ? sizeof(NmsSmem) : sizeof(MatchSmem)) + 15) & ~(size_t)15;
+constexpr size_t kMatchRegion = (sizeof(MatchSmem) + 15) & ~(size_t)15;
 
 __device__ __forceinline__ void load_gt_xyxy(const void* boxes, int dtype, int g, double& l, double& t, double& r, double& b) {
     if (dtype == KODB_BOXES_F64) {
@@ -323,59 +376,87 @@ __device__ __forceinline__ void load_gt_xyxy(const void* boxes, int dtype, int g
     }
 }
 
-__device__ void match_image(MatchSmem& ms, int nk, int C, const void* gt_boxes, const int64_t* gt_labels, int g0, int ng,
-                            int gt_dtype, const kodb_match_out& mo, int b, int max_det) {
-    const int tid = threadIdx.x;
-    for (int i = tid; i < nk; i += blockDim.x) ms.tp[i] = 0;
-    for (int i = tid; i < KODB_NUM_IOU_THRS * ng; i += blockDim.x) ms.taken[i / ng][i % ng] = 0;
-    for (int g = tid; g < ng; g += blockDim.x) {
+__device__ __forceinline__ void stage_gt(GtSmem& gs, int C, const void* gt_boxes, const int64_t* gt_labels, int g0, int ng,
+                                         int gt_dtype, const kodb_match_out& mo) {
+    for (int i = threadIdx.x; i < KODB_NUM_IOU_THRS * ng; i += blockDim.x) gs.taken[i / ng][i % ng] = 0;
+    for (int g = threadIdx.x; g < ng; g += blockDim.x) {
         const long long lab = gt_labels[g0 + g];
         if (lab >= 0 && lab < C) atomicAdd(reinterpret_cast<unsigned long long*>(mo.gt_count) + lab, 1ull);
         double l, t, r, bt;
         load_gt_xyxy(gt_boxes, gt_dtype, g0 + g, l, t, r, bt);
-        ms.gx[g] = l; ms.gy[g] = t; ms.gw[g] = r - l; ms.gh[g] = bt - t;  // [l, t, r-l, b-t]
-        ms.glabel[g] = (int)lab;
+        gs.gx[g] = l; gs.gy[g] = t; gs.gw[g] = r - l; gs.gh[g] = bt - t;  // [l, t, r-l, b-t]
+        gs.glabel[g] = (int)lab;
+    }
+}
+
+// maskApi.c::bbIou on [x,y,w,h] in fp64
+__device__ __forceinline__ double bb_iou(double dl, double dt, double dw, double dh, double da, const GtSmem& gs, int g) {
+    const double gl = gs.gx[g], gt_ = gs.gy[g], gw = gs.gw[g], gh = gs.gh[g];
+    const double iw = fmin(dl + dw, gl + gw) - fmax(dl, gl);
+    const double ih = fmin(dt + dh, gt_ + gh) - fmax(dt, gt_);
+    if (iw > 0 && ih > 0) {
+        const double i = iw * ih;
+        return i / (da + gw * gh - i);
+    }
+    return 0.0;
+}
+
+// Greedy COCO matching of the kept detections of one image (block-wide).  `gs` must have been staged.
+__device__ void match_image(MatchSmem& ms, GtSmem& gs, int nk, int C, int ng, const kodb_match_out& mo, int b, int max_det) {
+    const int tid = threadIdx.x;
+    double thr_min = 1.0;
+#pragma unroll
+    for (int t = 0; t < KODB_NUM_IOU_THRS; ++t) thr_min = fmin(thr_min, fmin(mo.iou_thrs[t], 1.0 - 1e-10));
+    // phase A (parallel over detections): which ground truths of its class does a detection overlap at all?
+    // Most detections overlap none and are false positives at every threshold; they drop out here.
+    const bool small = ng <= 64;
+    for (int d = tid; d < nk; d += blockDim.x) {
+        ms.tp[d] = 0;
+        unsigned long long mk = 0ull;
+        if (small) {
+            const int c = ms.cls[d];
+            const double dl = ms.x1[d], dt = ms.y1[d];
+            const double dw = (double)ms.x2[d] - dl, dh = (double)ms.y2[d] - dt;
+            const double da = dw * dh;
+            for (int g = 0; g < ng; ++g)
+                if (gs.glabel[g] == c && bb_iou(dl, dt, dw, dh, da, gs, g) >= thr_min) mk |= 1ull << g;
+        }
+        ms.gmask[d] = mk;
     }
     __syncthreads();
-    // One WARP per class (no divergence between classes): lane = (GT slice 0..7) x (IoU threshold 0..3).
-    // Detections of the class are visited sequentially in score order (the greedy dependency); for each one
-    // the 8 slices scan the class's free ground truths in parallel and a shuffle reduction picks the
+    // phase B: one WARP per class (no divergence between classes): lane = (GT slice 0..7) x (IoU threshold 0..3).
+    // The class's detections that overlap something are visited sequentially in score order (the greedy
+    // dependency); the 8 slices scan the free ground truths in parallel and a shuffle reduction picks the
     // pycocotools winner: largest IoU >= thr, ties -> the LATER ground truth.
     const int lane = tid & 31, wid = tid >> 5, nwarps = blockDim.x >> 5;
     const int t = lane & 3, sub = lane >> 2;
     const double thr = fmin(mo.iou_thrs[t], 1.0 - 1e-10);
     for (int c = wid; c < C; c += nwarps) {
-        // classes without ground truth in this image have nothing to match (all their detections are FP)
         bool has_gt = false;
-        for (int g = lane; g < ng; g += 32) has_gt |= (ms.glabel[g] == c);
-        if (!__any_sync(KODB_FULL_MASK, has_gt)) continue;
+        for (int g = lane; g < ng; g += 32) has_gt |= (gs.glabel[g] == c);
+        if (!__any_sync(KODB_FULL_MASK, has_gt)) continue;  // nothing to match: all detections of c are FP
         for (int d0 = 0; d0 < nk; d0 += 32) {
-            const int dc = (d0 + lane < nk) ? ms.cls[d0 + lane] : -1;
-            unsigned dm = __ballot_sync(KODB_FULL_MASK, dc == c);
+            const int dd = d0 + lane;
+            const bool cand = dd < nk && ms.cls[dd] == c && (!small || ms.gmask[dd] != 0ull);
+            unsigned dm = __ballot_sync(KODB_FULL_MASK, cand);
             while (dm) {
                 const int d = d0 + __ffs(dm) - 1;
                 dm &= dm - 1;
                 const double dl = ms.x1[d], dt = ms.y1[d];
                 const double dw = (double)ms.x2[d] - dl, dh = (double)ms.y2[d] - dt;
                 const double da = dw * dh;
+                const unsigned long long mk = small ? ms.gmask[d] : ~0ull;
                 double best = -1.0;
                 int m = -1;
                 for (int g = sub; g < ng; g += 8) {
-                    if (ms.glabel[g] != c || ms.taken[t][g]) continue;
-                    const double gl = ms.gx[g], gt_ = ms.gy[g], gw = ms.gw[g], gh = ms.gh[g];
-                    // maskApi.c::bbIou on [x,y,w,h]
-                    const double iw = fmin(dl + dw, gl + gw) - fmax(dl, gl);
-                    const double ih = fmin(dt + dh, gt_ + gh) - fmax(dt, gt_);
-                    double iou = 0.0;
-                    if (iw > 0 && ih > 0) {
-                        const double i = iw * ih;
-                        iou = i / (da + gw * gh - i);
-                    }
+                    if (small ? !((mk >> g) & 1ull) : (gs.glabel[g] != c)) continue;
+                    if (gs.taken[t][g]) continue;
+                    const double iou = bb_iou(dl, dt, dw, dh, da, gs, g);
                     if (iou < thr || iou < best) continue;
                     best = iou;  // ascending g inside a slice: a later equal IoU replaces the earlier one
                     m = g;
                 }
-                if (!__any_sync(KODB_FULL_MASK, m >= 0)) continue;  // no overlap >= any threshold: false positive
+                if (!__any_sync(KODB_FULL_MASK, m >= 0)) continue;
 #pragma unroll
                 for (int off = 4; off < 32; off <<= 1) {
                     const double ob = __shfl_xor_sync(KODB_FULL_MASK, best, off);
@@ -383,7 +464,7 @@ __device__ void match_image(MatchSmem& ms, int nk, int C, const void* gt_boxes, 
                     if (ob > best || (ob == best && om > m)) { best = ob; m = om; }
                 }
                 if (m >= 0 && sub == 0) {
-                    ms.taken[t][m] = 1;
+                    gs.taken[t][m] = 1;
                     atomicOr(&ms.tp[d], 1 << t);
                 }
                 __syncwarp();
@@ -404,6 +485,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NmsSmem& s = *reinterpret_cast<NmsSmem*>(smem_raw);
     MatchSmem& ms = *reinterpret_cast<MatchSmem*>(smem_raw);  // aliases NmsSmem: used after NMS is finished
+    GtSmem& gs = *reinterpret_cast<GtSmem*>(smem_raw + kNmsRegion);
 
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int C = p.C;
@@ -421,6 +503,13 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
     int trace_n = 0;
     KODB_TRACE(0);
     if (tid == 0) { s.nk = 0; }
+    // ground truth of the image -> shared memory now; the loads overlap the whole selection / NMS phase
+    int gt_n = 0;
+    if (p.do_match) {
+        const int g0 = p.gt_offsets[b];
+        gt_n = p.gt_offsets[b + 1] - g0;
+        stage_gt(gs, C, p.gt_boxes, p.gt_labels, g0, gt_n, p.gt_dtype, p.m);
+    }
     // coarse score histogram of the image (accumulated by the candidate kernel); reset for the next launch
     for (int i = tid; i < HB; i += NMS_THREADS) {
         s.chist[i] = p.hist[(int64_t)b * HB + i];
@@ -516,9 +605,19 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
         // ------------------------------------------------------------------ collect [lo, hi_batch)
         if (tid == 0) s.cnt = 0;
         __syncthreads();
-        for (int i = tid; i < n; i += NMS_THREADS) {
-            const unsigned long long ck = make_ck(score[i], key[i]);
-            if (ck >= lo && ck < hi_batch) s.sort_ck[atomicAdd(&s.cnt, 1)] = ck;
+        if ((uint32_t)lo == 0u && (hi_batch == U64MAX || (uint32_t)hi_batch == 0u)) {
+            // both bounds are score-bin boundaries: decide on the score alone, read the key of the selected only
+            const uint32_t dlo = (uint32_t)(lo >> 32), dhi = (uint32_t)(hi_batch >> 32);
+            const bool open_hi = hi_batch == U64MAX;
+            for (int i = tid; i < n; i += NMS_THREADS) {
+                const uint32_t dk = desc_key(score[i]);
+                if (dk >= dlo && (open_hi || dk < dhi)) s.sort_ck[atomicAdd(&s.cnt, 1)] = ((unsigned long long)dk << 32) | key[i];
+            }
+        } else {
+            for (int i = tid; i < n; i += NMS_THREADS) {
+                const unsigned long long ck = make_ck(score[i], key[i]);
+                if (ck >= lo && ck < hi_batch) s.sort_ck[atomicAdd(&s.cnt, 1)] = ck;
+            }
         }
         __syncthreads();
         KODB_TRACE(3);
@@ -563,47 +662,97 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
         }
         __syncthreads();
         KODB_TRACE(5);
-        // ------------------------------------------------------------------ greedy NMS, 32 candidates per step
-        for (int s0 = 0; s0 < mm && nk < max_det; s0 += 32) {
-            const int e = s0 + wid;  // warp `wid` owns candidate e
-            bool sup = false;
-            unsigned msk = 0u;
-            if (e < mm) {
-                const float cx1 = s.bx1[e], cy1 = s.by1[e], cx2 = s.bx2[e], cy2 = s.by2[e], ca = s.barea[e];
-                for (int q = lane; q < nk; q += 32)
-                    sup |= suppresses(s.kx1[q], s.ky1[q], s.kx2[q], s.ky2[q], s.karea[q], cx1, cy1, cx2, cy2, ca, iou_thr);
-                const int o = s0 + lane;
-                bool hit = false;
-                if (lane < wid && o < mm)
-                    hit = suppresses(s.bx1[o], s.by1[o], s.bx2[o], s.by2[o], s.barea[o], cx1, cy1, cx2, cy2, ca, iou_thr);
-                msk = __ballot_sync(KODB_FULL_MASK, hit);
+        // ------------------------------------------------------------------ greedy NMS, NMS_STEP candidates per step
+        // Warp w owns candidates 4w..4w+3 of the step.  (1) against the kept list: each kept box is loaded once
+        // and tested against the warp's four candidates; (2) against the earlier candidates of the same step: a
+        // 128x128 bit matrix built with ballots; (3) warp 0 resolves the step's triangular dependency by
+        // fixed-point iteration (exact: the only fixed point is the greedy solution) and appends the survivors.
+        for (int s0 = 0; s0 < mm && nk < max_det; s0 += NMS_STEP) {
+            float cb[4][5];
+            bool valid[4], sup[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int e = s0 + 4 * wid + r;
+                valid[r] = e < mm;
+                sup[r] = false;
+                const int ee = valid[r] ? e : 0;
+                cb[r][0] = s.bx1[ee]; cb[r][1] = s.by1[ee]; cb[r][2] = s.bx2[ee]; cb[r][3] = s.by2[ee]; cb[r][4] = s.barea[ee];
             }
-            const bool any = __any_sync(KODB_FULL_MASK, sup);
-            if (lane == 0) { s.alive[wid] = (e < mm) && !any; s.mask[wid] = msk; }
+            if (valid[0]) {
+                for (int q = lane; q < nk; q += 32) {
+                    const float k1 = s.kx1[q], k2 = s.ky1[q], k3 = s.kx2[q], k4 = s.ky2[q], ka = s.karea[q];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        sup[r] |= suppresses(k1, k2, k3, k4, ka, cb[r][0], cb[r][1], cb[r][2], cb[r][3], cb[r][4], iou_thr);
+                }
+            }
+            unsigned msk[4][NMS_STEP / 32];
+#pragma unroll
+            for (int i = 0; i < NMS_STEP / 32; ++i) {
+                const int oi = 32 * i + lane;  // index inside the step of the "other" candidate
+                const int o = s0 + oi;
+                const bool ov = o < mm && 32 * i < 4 * wid + 4;  // only earlier candidates matter
+                const int oo = ov ? o : 0;
+                const float o1 = s.bx1[oo], o2 = s.by1[oo], o3 = s.bx2[oo], o4 = s.by2[oo], oa = s.barea[oo];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const bool hit = ov && valid[r] && oi < 4 * wid + r &&
+                                     suppresses(o1, o2, o3, o4, oa, cb[r][0], cb[r][1], cb[r][2], cb[r][3], cb[r][4], iou_thr);
+                    msk[r][i] = __ballot_sync(KODB_FULL_MASK, hit);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const bool any = __any_sync(KODB_FULL_MASK, sup[r]);
+                if (lane == 0) {
+                    s.alive[4 * wid + r] = valid[r] && !any;
+#pragma unroll
+                    for (int i = 0; i < NMS_STEP / 32; ++i) s.mask[4 * wid + r][i] = msk[r][i];
+                }
+            }
             __syncthreads();
             if (wid == 0) {
-                // greedy resolution inside the block: kept_i = alive_i && no kept j < i suppresses i.  The
-                // triangular system is solved by fixed-point iteration with ballots (exact: its only fixed
-                // point is the greedy solution; converges in <= 32 rounds, typically 2-3)
-                const bool al = s.alive[lane] != 0;
-                const unsigned mk = s.mask[lane];
-                unsigned keptbits = __ballot_sync(KODB_FULL_MASK, al);
-                for (int it = 0; it < 33; ++it) {
-                    const unsigned nb = __ballot_sync(KODB_FULL_MASK, al && !(mk & keptbits));
-                    if (nb == keptbits) break;
-                    keptbits = nb;
+                // lane l looks after candidates l, l+32, l+64, l+96, so that ballot word i covers 32i..32i+31
+                bool al[NMS_STEP / 32];
+                unsigned mk[NMS_STEP / 32][NMS_STEP / 32], kept[NMS_STEP / 32];
+#pragma unroll
+                for (int i = 0; i < NMS_STEP / 32; ++i) {
+                    al[i] = s.alive[32 * i + lane] != 0;
+#pragma unroll
+                    for (int j = 0; j < NMS_STEP / 32; ++j) mk[i][j] = s.mask[32 * i + lane][j];
+                    kept[i] = __ballot_sync(KODB_FULL_MASK, al[i]);
                 }
-                if ((keptbits >> lane) & 1u) {
-                    const int slot = nk + __popc(keptbits & ((1u << lane) - 1u));
-                    if (slot < max_det) {
-                        const int o = s0 + lane;
-                        s.kx1[slot] = s.bx1[o]; s.ky1[slot] = s.by1[o]; s.kx2[slot] = s.bx2[o]; s.ky2[slot] = s.by2[o];
-                        s.karea[slot] = s.barea[o];
-                        s.kept_ck[slot] = s.sort_ck[o];
-                        s.kept_idx[slot] = processed + o;  // rank in the confidence-sorted list (rank mode)
+                for (int it = 0; it <= NMS_STEP; ++it) {
+                    unsigned nb[NMS_STEP / 32];
+                    bool same = true;
+#pragma unroll
+                    for (int i = 0; i < NMS_STEP / 32; ++i) {
+                        unsigned hit = 0u;
+#pragma unroll
+                        for (int j = 0; j < NMS_STEP / 32; ++j) hit |= mk[i][j] & kept[j];
+                        nb[i] = __ballot_sync(KODB_FULL_MASK, al[i] && !hit);
+                        same &= nb[i] == kept[i];
                     }
+#pragma unroll
+                    for (int i = 0; i < NMS_STEP / 32; ++i) kept[i] = nb[i];
+                    if (same) break;
                 }
-                if (lane == 0) s.nk = min(max_det, nk + __popc(keptbits));
+                int before = 0;
+#pragma unroll
+                for (int i = 0; i < NMS_STEP / 32; ++i) {
+                    if ((kept[i] >> lane) & 1u) {
+                        const int slot = nk + before + __popc(kept[i] & ((1u << lane) - 1u));
+                        if (slot < max_det) {
+                            const int o = s0 + 32 * i + lane;
+                            s.kx1[slot] = s.bx1[o]; s.ky1[slot] = s.by1[o]; s.kx2[slot] = s.bx2[o]; s.ky2[slot] = s.by2[o];
+                            s.karea[slot] = s.barea[o];
+                            s.kept_ck[slot] = s.sort_ck[o];
+                            s.kept_idx[slot] = processed + o;  // rank in the confidence-sorted list (rank mode)
+                        }
+                    }
+                    before += __popc(kept[i]);
+                }
+                if (lane == 0) s.nk = min(max_det, nk + before);
             }
             __syncthreads();
             nk = s.nk;
@@ -671,8 +820,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
             ms.score[tid] = rs; ms.cls[tid] = rc;
         }
         __syncthreads();
-        const int g0 = p.gt_offsets[b], ng = p.gt_offsets[b + 1] - g0;
-        match_image(ms, nk, C, p.gt_boxes, p.gt_labels, g0, ng, p.gt_dtype, p.m, b, max_det);
+        match_image(ms, gs, nk, C, gt_n, p.m, b, max_det);
     }
     KODB_TRACE(8);
 }
@@ -683,16 +831,18 @@ match_kernel(const float* __restrict__ dets, const int32_t* __restrict__ counts,
              const int64_t* gt_labels, const int32_t* gt_offsets, int gt_dtype, const __grid_constant__ kodb_match_out mo) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MatchSmem& ms = *reinterpret_cast<MatchSmem*>(smem_raw);
+    GtSmem& gs = *reinterpret_cast<GtSmem*>(smem_raw + kMatchRegion);
     const int b = blockIdx.x, tid = threadIdx.x;
     const int nk = min(counts[b], max_det);
+    const int g0 = gt_offsets[b], ng = gt_offsets[b + 1] - g0;
+    stage_gt(gs, C, gt_boxes, gt_labels, g0, ng, gt_dtype, mo);
     if (tid < nk) {
         const float* d = dets + ((int64_t)b * max_det + tid) * 6;
         ms.x1[tid] = d[0]; ms.y1[tid] = d[1]; ms.x2[tid] = d[2]; ms.y2[tid] = d[3];
         ms.score[tid] = d[4]; ms.cls[tid] = (int)d[5];
     }
     __syncthreads();
-    const int g0 = gt_offsets[b], ng = gt_offsets[b + 1] - g0;
-    match_image(ms, nk, C, gt_boxes, gt_labels, g0, ng, gt_dtype, mo, b, max_det);
+    match_image(ms, gs, nk, C, ng, mo, b, max_det);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -790,7 +940,7 @@ static long long* g_trace = nullptr;
 static int launch_select(const EvalParams& p_in, cudaStream_t st) {
     EvalParams p = p_in;
     p.trace = g_trace;
-    const size_t smem = sizeof(NmsSmem) > sizeof(MatchSmem) ? sizeof(NmsSmem) : sizeof(MatchSmem);
+    const size_t smem = kNmsRegion + sizeof(GtSmem);
     static bool attr_set[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -897,11 +1047,11 @@ extern "C" int kodb_map_match(const float* dets, const int32_t* counts, int32_t 
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        if (cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MatchSmem)) != cudaSuccess)
+        if (cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMatchRegion + sizeof(GtSmem))) != cudaSuccess)
             return KODB_ERR_LAUNCH;
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    match_kernel<<<batch, NMS_THREADS, sizeof(MatchSmem), (cudaStream_t)stream>>>(
+    match_kernel<<<batch, NMS_THREADS, kMatchRegion + sizeof(GtSmem), (cudaStream_t)stream>>>(
         dets, counts, num_classes, max_det, gt_h->boxes, gt_h->labels, gt_h->img_offsets, gt_h->boxes_dtype, *match_h);
     KODB_CHECK_LAUNCH();
     return KODB_OK;

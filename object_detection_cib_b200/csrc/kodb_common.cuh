@@ -52,9 +52,14 @@ __device__ __forceinline__ float exp_fast(float x) {  // |x| <= 87 (callers clam
     return fmaf(e, r * 0.693147182464599609375f, e);
 }
 // eval-side sigmoid (decode + candidate filter share it, so the fused path and get_detections agree bit for bit)
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float sigmoid_eval(float x) {
     const float t = fminf(fmaxf(-x, -87.0f), 87.0f);
-    return __frcp_rn(1.0f + exp_fast(t));
+    return rcp_approx(1.0f + exp_fast(t));
 }
 // softplus(x) and sigmoid(x) for the dense objectness pass
 __device__ __forceinline__ float softplus_sigmoid_fast(float x, float* sig) {
