@@ -118,10 +118,11 @@ __device__ __forceinline__ unsigned long long coarse_hi(int d) {
 // ---- geometry helpers -----------------------------------------------------------------------------------
 __device__ __forceinline__ void planar_tile(const EvalGeom& g, int t, int& L, int& a, int& c0, int& ncell) {
     L = t >= g.tile_begin[2] ? 2 : (t >= g.tile_begin[1] ? 1 : 0);
-    const int r = t - g.tile_begin[L];
+    int r = t - g.tile_begin[L];
     const int tpp = g.tiles_per_plane[L];
-    a = r / tpp;
-    c0 = (r - a * tpp) * g.tile_cells[L];
+    a = 0;
+    while (r >= tpp) { r -= tpp; ++a; }  // a < KODB_MAX_ANCHORS: cheaper than an integer division
+    c0 = r * g.tile_cells[L];
     ncell = min(g.tile_cells[L], g.lv[L].H * g.lv[L].W - c0);
 }
 __device__ __forceinline__ void planar_row(const EvalGeom& g, int row, int& L, int& a, int& cell) {
@@ -315,24 +316,244 @@ __global__ void __launch_bounds__(CAND_THREADS) cand_kernel(const __grid_constan
         if (s_hist[i]) atomicAdd(&p.hist[(int64_t)b * HB + i], s_hist[i]);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// 1b. warp-autonomous candidate kernel for the planar float4 case (the shipped fused path)
+// ---------------------------------------------------------------------------------------------------------
+// One WARP owns a tile of up to 128 contiguous cells of one (level, anchor) plane: lane l holds cells 4l..4l+3.
+// Every global load of the tile (the obj float4 and the NQ class float4s of the lane) is issued before the first
+// use, so one DRAM round trip covers the tile; there is no block-level barrier on the data path.  The per-pair
+// decision is one subtraction whose sign bit is funnel-shifted into a mask:  sigmoid(q)*o > thr  <=>  q > tau(o)
+// with tau = logit(thr/o) in exact arithmetic; pairs with |q - tau| <= TAU_WINDOW (a few per thousand) are
+// re-decided with the decode kernel's exact fp32 product, so the candidate set is the one kodb_decode + kodb_nms
+// would produce.  Flagged pairs become 16-bit ids in a warp-private shared list, then the warp writes them --
+// balanced, one pair per lane -- as (score, key) into one contiguous chunk claimed with a single atomicAdd.
+constexpr int WT_CELLS = 128;
+constexpr int CW_WARPS = 8;
+constexpr float TAU_WINDOW = 2.0e-4f;  // >> the ~1.5e-5 combined error of tau and of the fp32 product for thr/o < 0.9
+
+__device__ __forceinline__ unsigned long long expand_nibbles(unsigned a16) {  // bit u -> bits 4u..4u+3
+    unsigned long long x = a16 & 0xffffu;
+    x = (x | (x << 24)) & 0x000000ff000000ffull;
+    x = (x | (x << 12)) & 0x000f000f000f000full;
+    x = (x | (x << 6)) & 0x0303030303030303ull;
+    x = (x | (x << 3)) & 0x1111111111111111ull;
+    return x * 15ull;
+}
+
+template <int NQ>
+struct CandWarpSmem {  // one per warp: the kernel has no block-level barrier
+    float q[NQ][WT_CELLS];               // class logits of the tile (stash: candidates are re-read by id)
+    float o[WT_CELLS];                   // sigmoid(obj) per cell
+    unsigned hist[HB / 2];               // two 16-bit bins per word
+    unsigned short list[WT_CELLS * NQ];  // flagged (cell, class) ids
+};
+
+template <int NQ>
+__global__ void __launch_bounds__(CW_WARPS * 32, 2) cand_warp_kernel(const __grid_constant__ EvalParams p) {
+    extern __shared__ __align__(16) unsigned char cw_smem_raw[];
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    CandWarpSmem<NQ>& sm = reinterpret_cast<CandWarpSmem<NQ>*>(cw_smem_raw)[wid];
+    const int t = blockIdx.x * CW_WARPS + wid;
+    if (t >= p.tiles_per_image) return;
+    const int C = p.C;
+    const float thr = p.cfg.conf_thres;
+#pragma unroll
+    for (int i = 0; i < HB / 64; ++i) sm.hist[32 * i + lane] = 0u;
+    int L, a, c0, ncell;
+    planar_tile(p.g, t, L, a, c0, ncell);
+    const kodb_head_level& hd = p.g.head[L];
+    const int row0 = p.g.row_base[L] + a * (p.g.lv[L].H * p.g.lv[L].W) + c0;
+    const float* obj_base = hd.obj + (int64_t)b * hd.obj_sb + (int64_t)a * hd.obj_sa + c0;
+    const float* cls_base = hd.cls + (int64_t)b * hd.cls_sb + (int64_t)a * hd.cls_sa + c0;
+    const int64_t cls_step = hd.cls_sp;
+    const int cell0 = lane * 4;
+    const bool in_range = cell0 < ncell;  // tiles are multiples of 4 cells
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    constexpr unsigned CELL_MASK = (1u << NQ) - 1u;  // the NQ class bits of one cell
+    float4 q[NQ];
+    const float4 xo = in_range ? __ldg(reinterpret_cast<const float4*>(obj_base + cell0)) : zero4;
+    {
+        const int jn = min(C, CGROUP);
+        const float* cp = cls_base + cell0;
+#pragma unroll
+        for (int u = 0; u < NQ; ++u) {
+            q[u] = (in_range && u < jn) ? __ldg(reinterpret_cast<const float4*>(cp)) : zero4;
+            cp += cls_step;
+        }
+    }
+    // per cell: objectness, row filter (nms.py:33) and the class-logit threshold (branch-free)
+    float tau[4];
+    unsigned force = 0u;  // cells whose passing pairs all take the exact test
+    {
+        const float x[4] = {xo.x, xo.y, xo.z, xo.w};
+        float ov4[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const float ov = sigmoid_eval(x[v]);
+            ov4[v] = ov;
+            const bool act = in_range && ov > thr;
+            const float r = thr * rcp_approx(ov);  // thr / o, in (0, 1) for an active cell
+            const bool fast = act && thr > 0.0f && r < 0.9f;
+            const float tv = 0.693147182464599609375f * lg2_approx(r * rcp_approx(1.0f - r));  // logit(thr / o)
+            // r >= 0.9 (o barely above thr; logit ill-conditioned): the true threshold is >= logit(0.9) = 2.197, so
+            // 2.19 is a safe lower bound -- the (very few) pairs above it are re-decided exactly.  thr <= 0: all are.
+            const float slow_tau = thr > 0.0f ? 2.19f : -3.0e38f;
+            tau[v] = act ? (fast ? tv : slow_tau) : 3.0e38f;  // inactive cell: nothing passes
+            if (act && !fast) force |= 1u << v;
+        }
+        *reinterpret_cast<float4*>(&sm.o[cell0]) = make_float4(ov4[0], ov4[1], ov4[2], ov4[3]);
+    }
+    float* sc_img = p.cand_score + (int64_t)b * p.cand_stride;
+    uint32_t* ky_img = p.cand_key + (int64_t)b * p.cand_stride;
+    for (int grp = 0; grp < p.ngroups; ++grp) {
+        const int j0 = grp * CGROUP, jn = min(C - j0, CGROUP);
+        if (grp > 0) {
+            const float* cp = cls_base + (int64_t)j0 * cls_step + cell0;
+#pragma unroll
+            for (int u = 0; u < NQ; ++u) {
+                q[u] = (in_range && u < jn) ? __ldg(reinterpret_cast<const float4*>(cp)) : zero4;
+                cp += cls_step;
+            }
+        }
+        // pair (u, v): the sign bit of (tau[v] - q[u][v]) is funnel-shifted into one mask per cell (four
+        // independent dependency chains); class u ends at bit NQ-1-u of the chain
+        unsigned mv[4] = {0u, 0u, 0u, 0u};
+        float amin = 3.0e38f;
+#pragma unroll
+        for (int u = 0; u < NQ; ++u) {
+            *reinterpret_cast<float4*>(&sm.q[u][cell0]) = q[u];
+            const float qq[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const float d = tau[v] - qq[v];
+                mv[v] = __funnelshift_l(__float_as_uint(d), mv[v], 1);
+                amin = fminf(amin, fabsf(d));
+            }
+        }
+        unsigned cm[4];  // cm[v] bit u: pair (class j0+u, cell cell0+v) is a candidate
+        unsigned fany = 0u;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            cm[v] = __brev(mv[v]) >> (32 - NQ);
+            if ((force >> v) & 1u) fany |= cm[v];
+        }
+        if (amin <= TAU_WINDOW || fany) {  // rare: re-decide the borderline pairs with the decode kernel's arithmetic
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                unsigned border = ((force >> v) & 1u) ? cm[v] : 0u;  // forced cell: every pair above the conservative bound
+#pragma unroll
+                for (int u = 0; u < NQ; ++u) {
+                    if (fabsf(tau[v] - sm.q[u][cell0 + v]) <= TAU_WINDOW) border |= 1u << u;  // (own stash: no sync needed)
+                }
+                const float ov = sm.o[cell0 + v];
+                while (border) {
+                    const int u = __ffs(border) - 1;
+                    border &= border - 1;
+                    cm[v] &= ~(1u << u);
+                    if (ov > thr && sigmoid_eval(sm.q[u][cell0 + v]) * ov > thr) cm[v] |= 1u << u;
+                }
+            }
+        }
+        // classes beyond the group's end and the `classes` filter (nms.py:54-55)
+        const unsigned am = (p.cfg.class_mask[j0 >> 5] >> (j0 & 31)) & ((1u << jn) - 1u) & CELL_MASK;
+        int mine = 0;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            cm[v] &= am;
+            mine += __popc(cm[v]);
+        }
+        int slot = warp_excl_scan_i(mine, lane);
+        const int n = __shfl_sync(KODB_FULL_MASK, slot + mine, 31);
+        {  // fully predicated (no per-lane loops: the lanes' candidate counts differ by 2x and more)
+            unsigned short* lp = sm.list + slot;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const int idb = (cell0 + v) << 4;
+#pragma unroll
+                for (int u = 0; u < NQ; ++u)
+                    if (cm[v] & (1u << u)) *lp++ = (unsigned short)(idb | u);
+            }
+        }
+        int base = 0;
+        if (lane == 0) {
+            const int64_t chunk = (int64_t)b * p.chunks_per_image + (int64_t)t * p.ngroups + grp;
+            base = n ? atomicAdd(&p.img_count[b], n) : 0;
+            p.chunk_start[chunk] = base;
+            p.chunk_count[chunk] = n;
+        }
+        base = __shfl_sync(KODB_FULL_MASK, base, 0);
+        __syncwarp();  // list, q stash and o are visible to the whole warp
+        float* scp = sc_img + base;
+        uint32_t* kyp = ky_img + base;
+        const uint32_t key0 = (uint32_t)row0 * (uint32_t)C + (uint32_t)j0;
+#pragma unroll 1
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            if (i < n) {
+                const int pid = sm.list[i];
+                const int cl = pid >> 4, u = pid & 15;
+                const float conf = sigmoid_eval(sm.q[u][cl]) * sm.o[cl];  // the decode kernel's arithmetic
+                scp[i] = conf;
+                kyp[i] = key0 + (uint32_t)cl * (uint32_t)C + (uint32_t)u;
+                const int bin = coarse_bin(conf);  // a warp adds < 65536 candidates: the 16-bit halves cannot overflow
+                atomicAdd(&sm.hist[bin >> 1], 1u << ((bin & 1) << 4));
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int i = 0; i < HB / 64; ++i) {
+        const unsigned v = sm.hist[32 * i + lane];
+        int* gh = p.hist + (int64_t)b * HB + 2 * (32 * i + lane);
+        if (v & 0xffffu) atomicAdd(gh, (int)(v & 0xffffu));
+        if (v >> 16) atomicAdd(gh + 1, (int)(v >> 16));
+    }
+}
+
+template <int NQ>
+static int launch_cand_warp(const EvalParams& p, dim3 grid, cudaStream_t st) {
+    const size_t smem = sizeof(CandWarpSmem<NQ>) * CW_WARPS;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        if (cudaFuncSetAttribute(cand_warp_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return KODB_ERR_LAUNCH;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    cand_warp_kernel<NQ><<<grid, CW_WARPS * 32, smem, st>>>(p);
+    KODB_CHECK_LAUNCH();
+    return KODB_OK;
+}
+
 // =========================================================================================================
 // 2. per-image select + NMS (+ matching)
 // =========================================================================================================
+constexpr int CLS_CAP = 256;             // class-bucketed NMS: max candidates of ONE class in a batch
+constexpr int CLS_WORDS = CLS_CAP / 32;  // suppression-mask words per candidate
+
 struct NmsSmem {
-    int hist[NB];
+    int hist[NB];  // fine histogram of the radix refinement; aliased by the per-(warp, class) counts of the NMS phase
     int chist[HB];
     int cprefix[CHUNK_CAP];
     unsigned long long sort_ck[K_CAP];
-    float bx1[K_CAP], by1[K_CAP], bx2[K_CAP], by2[K_CAP], barea[K_CAP];
+    float bx1[K_CAP], by1[K_CAP], bx2[K_CAP], by2[K_CAP], barea[K_CAP];      // batch, score order
+    float cx1[K_CAP], cy1[K_CAP], cx2[K_CAP], cy2[K_CAP], carea[K_CAP];      // batch, class-major order
+    unsigned pm[K_CAP * CLS_WORDS];  // pm[pos][J]: earlier same-class candidates 32J..32J+31 that suppress `pos`
+    unsigned char pre[K_CAP], keepf[K_CAP];
+    int ccount[KODB_MAX_CLASSES], cbase[KODB_MAX_CLASSES], tstart[KODB_MAX_CLASSES + 1];
     float kx1[MAX_DET_CAP], ky1[MAX_DET_CAP], kx2[MAX_DET_CAP], ky2[MAX_DET_CAP], karea[MAX_DET_CAP];
+    int kcls[MAX_DET_CAP];
     unsigned long long kept_ck[MAX_DET_CAP];
     long long kept_idx[MAX_DET_CAP];
     int scan_tmp[33];
     int alive[NMS_STEP];
     unsigned mask[NMS_STEP][NMS_STEP / 32];
     int sel_bin, sel_p, sel_prev;
-    int cnt, nk;
+    int cnt, nk, cls_over;
 };
+static_assert(sizeof(NmsSmem) + sizeof(unsigned long long) * 0 <= 200 * 1024, "NmsSmem budget");
+static_assert(NB >= 32 * KODB_MAX_CLASSES, "per-(warp, class) counts alias the fine histogram");
 
 __device__ __forceinline__ bool suppresses(float ax1, float ay1, float ax2, float ay2, float aarea, float bx1, float by1,
                                            float bx2, float by2, float barea, double thr) {
@@ -503,6 +724,12 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
     int trace_n = 0;
     KODB_TRACE(0);
     if (tid == 0) { s.nk = 0; }
+    // Class-bucketed NMS is exact iff boxes of different classes cannot intersect after the class offset: every
+    // raw coordinate inside a window no wider than max_wh, class offsets j*max_wh exact in fp32 (rounding of
+    // x + offset is monotone, so disjoint stays disjoint), and a threshold >= 0 (zero overlap never suppresses).
+    const float win_lo = -0.25f * max_wh, win_hi = 0.75f * max_wh;
+    bool cls_static = iou_thr >= 0.0 && max_wh > 0.0f && max_wh < 3.0e38f && (double)win_hi - (double)win_lo <= (double)max_wh;
+    cls_static = __syncthreads_and(tid >= C || (double)((float)tid * max_wh) == (double)tid * (double)max_wh) && cls_static;
     // ground truth of the image -> shared memory now; the loads overlap the whole selection / NMS phase
     int gt_n = 0;
     if (p.do_match) {
@@ -606,12 +833,47 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
         if (tid == 0) s.cnt = 0;
         __syncthreads();
         if ((uint32_t)lo == 0u && (hi_batch == U64MAX || (uint32_t)hi_batch == 0u)) {
-            // both bounds are score-bin boundaries: decide on the score alone, read the key of the selected only
+            // both bounds are score-bin boundaries: decide on the score alone, read the key of the selected only.
+            // float4 loads, four in flight per thread; pushes are warp-aggregated (one shared atomic per warp).
             const uint32_t dlo = (uint32_t)(lo >> 32), dhi = (uint32_t)(hi_batch >> 32);
             const bool open_hi = hi_batch == U64MAX;
-            for (int i = tid; i < n; i += NMS_THREADS) {
-                const uint32_t dk = desc_key(score[i]);
-                if (dk >= dlo && (open_hi || dk < dhi)) s.sort_ck[atomicAdd(&s.cnt, 1)] = ((unsigned long long)dk << 32) | key[i];
+            const float4* score4 = reinterpret_cast<const float4*>(score);  // cand_stride is a multiple of 4
+            const int n4 = (n + 3) >> 2;
+            const float ninf = __int_as_float(0xff800000);
+            for (int r0 = 0; r0 < n4; r0 += 4 * NMS_THREADS) {
+                float4 sv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = r0 + u * NMS_THREADS + tid;
+                    sv[u] = i < n4 ? __ldg(score4 + i) : make_float4(ninf, ninf, ninf, ninf);
+                }
+                unsigned take = 0u;  // bit 4u + w
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = 4 * (r0 + u * NMS_THREADS + tid);
+                    const float vv[4] = {sv[u].x, sv[u].y, sv[u].z, sv[u].w};
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        const uint32_t dk = desc_key(vv[w]);
+                        if (i + w < n && dk >= dlo && (open_hi || dk < dhi)) take |= 1u << (4 * u + w);
+                    }
+                }
+                if (__ballot_sync(KODB_FULL_MASK, take != 0u)) {  // one shared atomic per warp and round
+                    const int mine = __popc(take);
+                    const int ex = warp_excl_scan_i(mine, lane);
+                    int base = 0;
+                    if (lane == 31) base = atomicAdd(&s.cnt, ex + mine);
+                    int pos = __shfl_sync(KODB_FULL_MASK, base, 31) + ex;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = 4 * (r0 + u * NMS_THREADS + tid);
+                        const float vv[4] = {sv[u].x, sv[u].y, sv[u].z, sv[u].w};
+#pragma unroll
+                        for (int w = 0; w < 4; ++w)
+                            if ((take >> (4 * u + w)) & 1u)
+                                s.sort_ck[pos++] = ((unsigned long long)desc_key(vv[w]) << 32) | __ldg(key + i + w);
+                    }
+                }
             }
         } else {
             for (int i = tid; i < n; i += NMS_THREADS) {
@@ -651,111 +913,251 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
         int mm = m;
         if (processed + mm > limit) mm = limit - processed;  // only the top max_nms enter NMS
         // ------------------------------------------------------------------ decode the batch (offset boxes)
-        for (int e = tid; e < mm; e += NMS_THREADS) {
-            const uint32_t k32 = (uint32_t)s.sort_ck[e];
+        // one candidate per thread (mm <= K_CAP == NMS_THREADS); `bad`: a raw coordinate outside the window in which
+        // boxes of different classes provably cannot overlap after the class offset (nms.py:66)
+        int my_c = -1;
+        bool bad = false;
+        if (tid < mm) {
+            const uint32_t k32 = (uint32_t)s.sort_ck[tid];
             const int row = (int)(k32 / (uint32_t)C), j = (int)(k32 - (uint32_t)row * (uint32_t)C);
             const float4 bx = fetch_box(p, b, row);
             const float off = (float)j * max_wh;  // nms.py:66
             const float x1 = bx.x + off, y1 = bx.y + off, x2 = bx.z + off, y2 = bx.w + off;
-            s.bx1[e] = x1; s.by1[e] = y1; s.bx2[e] = x2; s.by2[e] = y2;
-            s.barea[e] = (x2 - x1) * (y2 - y1);
+            s.bx1[tid] = x1; s.by1[tid] = y1; s.bx2[tid] = x2; s.by2[tid] = y2;
+            s.barea[tid] = (x2 - x1) * (y2 - y1);
+            my_c = j;
+            bad = !(bx.x >= win_lo && bx.x <= win_hi && bx.y >= win_lo && bx.y <= win_hi && bx.z >= win_lo && bx.z <= win_hi &&
+                    bx.w >= win_lo && bx.w <= win_hi);
         }
-        __syncthreads();
+        if (cls_static) {
+            for (int i = tid; i < 32 * C; i += NMS_THREADS) s.hist[i] = 0;  // per-(warp, class) counts
+        }
+        if (__syncthreads_or(bad)) cls_static = false;  // sticky: a kept out-of-window box may reach across classes later
+        bool cls_path = cls_static;
         KODB_TRACE(5);
-        // ------------------------------------------------------------------ greedy NMS, NMS_STEP candidates per step
-        // Warp w owns candidates 4w..4w+3 of the step.  (1) against the kept list: each kept box is loaded once
-        // and tested against the warp's four candidates; (2) against the earlier candidates of the same step: a
-        // 128x128 bit matrix built with ballots; (3) warp 0 resolves the step's triangular dependency by
-        // fixed-point iteration (exact: the only fixed point is the greedy solution) and appends the survivors.
-        for (int s0 = 0; s0 < mm && nk < max_det; s0 += NMS_STEP) {
-            float cb[4][5];
-            bool valid[4], sup[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int e = s0 + 4 * wid + r;
-                valid[r] = e < mm;
-                sup[r] = false;
-                const int ee = valid[r] ? e : 0;
-                cb[r][0] = s.bx1[ee]; cb[r][1] = s.by1[ee]; cb[r][2] = s.bx2[ee]; cb[r][3] = s.by2[ee]; cb[r][4] = s.barea[ee];
-            }
-            if (valid[0]) {
-                for (int q = lane; q < nk; q += 32) {
-                    const float k1 = s.kx1[q], k2 = s.ky1[q], k3 = s.kx2[q], k4 = s.ky2[q], ka = s.karea[q];
-#pragma unroll
-                    for (int r = 0; r < 4; ++r)
-                        sup[r] |= suppresses(k1, k2, k3, k4, ka, cb[r][0], cb[r][1], cb[r][2], cb[r][3], cb[r][4], iou_thr);
-                }
-            }
-            unsigned msk[4][NMS_STEP / 32];
-#pragma unroll
-            for (int i = 0; i < NMS_STEP / 32; ++i) {
-                const int oi = 32 * i + lane;  // index inside the step of the "other" candidate
-                const int o = s0 + oi;
-                const bool ov = o < mm && 32 * i < 4 * wid + 4;  // only earlier candidates matter
-                const int oo = ov ? o : 0;
-                const float o1 = s.bx1[oo], o2 = s.by1[oo], o3 = s.bx2[oo], o4 = s.by2[oo], oa = s.barea[oo];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const bool hit = ov && valid[r] && oi < 4 * wid + r &&
-                                     suppresses(o1, o2, o3, o4, oa, cb[r][0], cb[r][1], cb[r][2], cb[r][3], cb[r][4], iou_thr);
-                    msk[r][i] = __ballot_sync(KODB_FULL_MASK, hit);
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const bool any = __any_sync(KODB_FULL_MASK, sup[r]);
-                if (lane == 0) {
-                    s.alive[4 * wid + r] = valid[r] && !any;
-#pragma unroll
-                    for (int i = 0; i < NMS_STEP / 32; ++i) s.mask[4 * wid + r][i] = msk[r][i];
-                }
+        // ------------------------------------------------------------------ greedy NMS
+        // Class-bucketed path.  After the class offset, boxes of different classes never intersect, so greedy NMS
+        // factorises per class; only the cut at max_det keeps couples the classes, and it is taken afterwards in
+        // score order.  (1) stable bucketing of the batch by class (match.any + per-warp counts); (2) per class,
+        // 32x32 tiles of the lower-triangular "j suppresses i" matrix, one tile per warp, as bit masks; (3) one warp
+        // per class resolves the greedy recurrence 32 candidates at a time (fixed-point iteration: its only fixed
+        // point is the greedy solution); (4) survivors are appended in score order.  Falls back to the generic
+        // step loop below when a class has more than CLS_CAP candidates in the batch or the window test failed.
+        int my_pos = 0;
+        if (cls_path) {
+            const unsigned peers = __match_any_sync(KODB_FULL_MASK, my_c);
+            const int rank = __popc(peers & ((1u << lane) - 1u));
+            if (my_c >= 0 && rank == 0) s.hist[wid * C + my_c] = __popc(peers);
+            __syncthreads();
+            for (int c = wid; c < C; c += NMS_THREADS / 32) {  // exclusive prefix over the warps, per class (lane = warp)
+                const int v = s.hist[lane * C + c];
+                const int ex = warp_excl_scan_i(v, lane);
+                s.hist[lane * C + c] = ex;
+                if (lane == 31) s.ccount[c] = ex + v;
             }
             __syncthreads();
-            if (wid == 0) {
-                // lane l looks after candidates l, l+32, l+64, l+96, so that ballot word i covers 32i..32i+31
-                bool al[NMS_STEP / 32];
-                unsigned mk[NMS_STEP / 32][NMS_STEP / 32], kept[NMS_STEP / 32];
-#pragma unroll
-                for (int i = 0; i < NMS_STEP / 32; ++i) {
-                    al[i] = s.alive[32 * i + lane] != 0;
-#pragma unroll
-                    for (int j = 0; j < NMS_STEP / 32; ++j) mk[i][j] = s.mask[32 * i + lane][j];
-                    kept[i] = __ballot_sync(KODB_FULL_MASK, al[i]);
+            if (wid == 0) {  // class bases, tile starts, capacity check
+                int run_c = 0, run_t = 0;
+                bool over = false;
+                for (int c0 = 0; c0 < C; c0 += 32) {
+                    const int c = c0 + lane;
+                    const int cnt = c < C ? s.ccount[c] : 0;
+                    const int nb = (cnt + 31) >> 5, tl = nb * (nb + 1) / 2;
+                    const int ex = warp_excl_scan_i(cnt, lane), tex = warp_excl_scan_i(tl, lane);
+                    if (c < C) { s.cbase[c] = run_c + ex; s.tstart[c] = run_t + tex; }
+                    run_c += __shfl_sync(KODB_FULL_MASK, ex + cnt, 31);
+                    run_t += __shfl_sync(KODB_FULL_MASK, tex + tl, 31);
+                    over |= cnt > CLS_CAP;
                 }
-                for (int it = 0; it <= NMS_STEP; ++it) {
-                    unsigned nb[NMS_STEP / 32];
-                    bool same = true;
-#pragma unroll
-                    for (int i = 0; i < NMS_STEP / 32; ++i) {
-                        unsigned hit = 0u;
-#pragma unroll
-                        for (int j = 0; j < NMS_STEP / 32; ++j) hit |= mk[i][j] & kept[j];
-                        nb[i] = __ballot_sync(KODB_FULL_MASK, al[i] && !hit);
-                        same &= nb[i] == kept[i];
-                    }
-#pragma unroll
-                    for (int i = 0; i < NMS_STEP / 32; ++i) kept[i] = nb[i];
-                    if (same) break;
+                over = __any_sync(KODB_FULL_MASK, over);
+                if (lane == 0) { s.tstart[C] = run_t; s.cls_over = over; }
+            }
+            __syncthreads();
+            cls_path = !s.cls_over;
+            if (cls_path) {
+                if (my_c >= 0) {
+                    my_pos = s.cbase[my_c] + s.hist[wid * C + my_c] + rank;
+                    const float x1 = s.bx1[tid], y1 = s.by1[tid], x2 = s.bx2[tid], y2 = s.by2[tid], ar = s.barea[tid];
+                    s.cx1[my_pos] = x1; s.cy1[my_pos] = y1; s.cx2[my_pos] = x2; s.cy2[my_pos] = y2; s.carea[my_pos] = ar;
+                    bool dead = false;  // suppressed by a survivor of an earlier batch (same class only)
+                    for (int q = 0; q < nk && !dead; ++q)
+                        dead = s.kcls[q] == my_c && suppresses(s.kx1[q], s.ky1[q], s.kx2[q], s.ky2[q], s.karea[q], x1, y1, x2, y2, ar, iou_thr);
+                    s.pre[my_pos] = dead;
                 }
-                int before = 0;
-#pragma unroll
-                for (int i = 0; i < NMS_STEP / 32; ++i) {
-                    if ((kept[i] >> lane) & 1u) {
-                        const int slot = nk + before + __popc(kept[i] & ((1u << lane) - 1u));
-                        if (slot < max_det) {
-                            const int o = s0 + 32 * i + lane;
-                            s.kx1[slot] = s.bx1[o]; s.ky1[slot] = s.by1[o]; s.kx2[slot] = s.bx2[o]; s.ky2[slot] = s.by2[o];
-                            s.karea[slot] = s.barea[o];
-                            s.kept_ck[slot] = s.sort_ck[o];
-                            s.kept_idx[slot] = processed + o;  // rank in the confidence-sorted list (rank mode)
+                __syncthreads();
+                const int T = s.tstart[C];
+                for (int tt = wid; tt < T; tt += NMS_THREADS / 32) {
+                    int c = 0;
+                    {
+                        int hi_ = C - 1;
+                        while (c < hi_) {  // largest c with tstart[c] <= tt
+                            const int mid = (c + hi_ + 1) >> 1;
+                            if (s.tstart[mid] <= tt) c = mid; else hi_ = mid - 1;
                         }
                     }
-                    before += __popc(kept[i]);
+                    const int k = tt - s.tstart[c];
+                    int I = 0;
+                    while ((I + 1) * (I + 2) / 2 <= k) ++I;
+                    const int J = k - I * (I + 1) / 2;
+                    const int base = s.cbase[c], nc = s.ccount[c];
+                    const int i = 32 * I + lane;
+                    const bool vi = i < nc;
+                    const int pi = base + (vi ? i : 0);
+                    const float i1 = s.cx1[pi], i2 = s.cy1[pi], i3 = s.cx2[pi], i4 = s.cy2[pi], ia = s.carea[pi];
+                    const int jend = min(32, min(nc, 32 * I + 31) - 32 * J);  // j < i <= 32I+31
+                    unsigned word = 0u;
+                    for (int jj = 0; jj < jend; ++jj) {
+                        const int pj = base + 32 * J + jj;
+                        const bool hit = vi && (32 * J + jj < i) &&
+                                         suppresses(s.cx1[pj], s.cy1[pj], s.cx2[pj], s.cy2[pj], s.carea[pj], i1, i2, i3, i4, ia, iou_thr);
+                        word |= (unsigned)hit << jj;
+                    }
+                    if (vi) s.pm[(size_t)pi * CLS_WORDS + J] = word;
                 }
-                if (lane == 0) s.nk = min(max_det, nk + before);
+                __syncthreads();
+                for (int c = wid; c < C; c += NMS_THREADS / 32) {
+                    const int nc = s.ccount[c];
+                    if (nc == 0) continue;
+                    const int base = s.cbase[c], nb = (nc + 31) >> 5;
+                    unsigned kw[CLS_WORDS];
+#pragma unroll
+                    for (int I = 0; I < CLS_WORDS; ++I) {
+                        kw[I] = 0u;
+                        if (I < nb) {
+                            const int i = 32 * I + lane;
+                            const bool vi = i < nc;
+                            const int pi = base + (vi ? i : 0);
+                            bool dead = !vi || s.pre[pi];
+#pragma unroll
+                            for (int J = 0; J < CLS_WORDS; ++J)
+                                if (J < I) dead |= (s.pm[(size_t)pi * CLS_WORDS + J] & kw[J]) != 0u;
+                            const unsigned diag = vi ? s.pm[(size_t)pi * CLS_WORDS + I] : 0u;
+                            unsigned cur = __ballot_sync(KODB_FULL_MASK, !dead);
+                            for (int it = 0; it < 33; ++it) {
+                                const unsigned nxt = __ballot_sync(KODB_FULL_MASK, !dead && !(diag & cur));
+                                if (nxt == cur) break;
+                                cur = nxt;
+                            }
+                            kw[I] = cur;
+                            if (vi) s.keepf[pi] = (cur >> lane) & 1u;
+                        }
+                    }
+                }
+                __syncthreads();
+                const int kf = (my_c >= 0 && s.keepf[my_pos]) ? 1 : 0;
+                int tot;
+                const int ex = block_excl_scan(kf, s.scan_tmp, &tot);
+                if (kf) {
+                    const int slot = nk + ex;
+                    if (slot < max_det) {
+                        s.kx1[slot] = s.bx1[tid]; s.ky1[slot] = s.by1[tid]; s.kx2[slot] = s.bx2[tid]; s.ky2[slot] = s.by2[tid];
+                        s.karea[slot] = s.barea[tid];
+                        s.kcls[slot] = my_c;
+                        s.kept_ck[slot] = s.sort_ck[tid];
+                        s.kept_idx[slot] = processed + tid;  // rank in the confidence-sorted list (rank mode)
+                    }
+                }
+                nk = min(max_det, nk + tot);
+                __syncthreads();
             }
-            __syncthreads();
-            nk = s.nk;
+        }
+        if (!cls_path) {
+            // Generic path, NMS_STEP candidates per step.
+            // Warp w owns candidates 4w..4w+3 of the step.  (1) against the kept list: each kept box is loaded once
+            // and tested against the warp's four candidates; (2) against the earlier candidates of the same step: a
+            // 128x128 bit matrix built with ballots; (3) warp 0 resolves the step's triangular dependency by
+            // fixed-point iteration (exact: the only fixed point is the greedy solution) and appends the survivors.
+            for (int s0 = 0; s0 < mm && nk < max_det; s0 += NMS_STEP) {
+                float cb[4][5];
+                bool valid[4], sup[4];
+    #pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int e = s0 + 4 * wid + r;
+                    valid[r] = e < mm;
+                    sup[r] = false;
+                    const int ee = valid[r] ? e : 0;
+                    cb[r][0] = s.bx1[ee]; cb[r][1] = s.by1[ee]; cb[r][2] = s.bx2[ee]; cb[r][3] = s.by2[ee]; cb[r][4] = s.barea[ee];
+                }
+                if (valid[0]) {
+                    for (int q = lane; q < nk; q += 32) {
+                        const float k1 = s.kx1[q], k2 = s.ky1[q], k3 = s.kx2[q], k4 = s.ky2[q], ka = s.karea[q];
+    #pragma unroll
+                        for (int r = 0; r < 4; ++r)
+                            sup[r] |= suppresses(k1, k2, k3, k4, ka, cb[r][0], cb[r][1], cb[r][2], cb[r][3], cb[r][4], iou_thr);
+                    }
+                }
+                unsigned msk[4][NMS_STEP / 32];
+    #pragma unroll
+                for (int i = 0; i < NMS_STEP / 32; ++i) {
+                    const int oi = 32 * i + lane;  // index inside the step of the "other" candidate
+                    const int o = s0 + oi;
+                    const bool ov = o < mm && 32 * i < 4 * wid + 4;  // only earlier candidates matter
+                    const int oo = ov ? o : 0;
+                    const float o1 = s.bx1[oo], o2 = s.by1[oo], o3 = s.bx2[oo], o4 = s.by2[oo], oa = s.barea[oo];
+    #pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const bool hit = ov && valid[r] && oi < 4 * wid + r &&
+                                         suppresses(o1, o2, o3, o4, oa, cb[r][0], cb[r][1], cb[r][2], cb[r][3], cb[r][4], iou_thr);
+                        msk[r][i] = __ballot_sync(KODB_FULL_MASK, hit);
+                    }
+                }
+    #pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const bool any = __any_sync(KODB_FULL_MASK, sup[r]);
+                    if (lane == 0) {
+                        s.alive[4 * wid + r] = valid[r] && !any;
+    #pragma unroll
+                        for (int i = 0; i < NMS_STEP / 32; ++i) s.mask[4 * wid + r][i] = msk[r][i];
+                    }
+                }
+                __syncthreads();
+                if (wid == 0) {
+                    // lane l looks after candidates l, l+32, l+64, l+96, so that ballot word i covers 32i..32i+31
+                    bool al[NMS_STEP / 32];
+                    unsigned mk[NMS_STEP / 32][NMS_STEP / 32], kept[NMS_STEP / 32];
+    #pragma unroll
+                    for (int i = 0; i < NMS_STEP / 32; ++i) {
+                        al[i] = s.alive[32 * i + lane] != 0;
+    #pragma unroll
+                        for (int j = 0; j < NMS_STEP / 32; ++j) mk[i][j] = s.mask[32 * i + lane][j];
+                        kept[i] = __ballot_sync(KODB_FULL_MASK, al[i]);
+                    }
+                    for (int it = 0; it <= NMS_STEP; ++it) {
+                        unsigned nb[NMS_STEP / 32];
+                        bool same = true;
+    #pragma unroll
+                        for (int i = 0; i < NMS_STEP / 32; ++i) {
+                            unsigned hit = 0u;
+    #pragma unroll
+                            for (int j = 0; j < NMS_STEP / 32; ++j) hit |= mk[i][j] & kept[j];
+                            nb[i] = __ballot_sync(KODB_FULL_MASK, al[i] && !hit);
+                            same &= nb[i] == kept[i];
+                        }
+    #pragma unroll
+                        for (int i = 0; i < NMS_STEP / 32; ++i) kept[i] = nb[i];
+                        if (same) break;
+                    }
+                    int before = 0;
+    #pragma unroll
+                    for (int i = 0; i < NMS_STEP / 32; ++i) {
+                        if ((kept[i] >> lane) & 1u) {
+                            const int slot = nk + before + __popc(kept[i] & ((1u << lane) - 1u));
+                            if (slot < max_det) {
+                                const int o = s0 + 32 * i + lane;
+                                s.kx1[slot] = s.bx1[o]; s.ky1[slot] = s.by1[o]; s.kx2[slot] = s.bx2[o]; s.ky2[slot] = s.by2[o];
+                                s.karea[slot] = s.barea[o];
+                                s.kept_ck[slot] = s.sort_ck[o];
+                                s.kcls[slot] = (int)((uint32_t)s.sort_ck[o] % (uint32_t)C);
+                                s.kept_idx[slot] = processed + o;  // rank in the confidence-sorted list (rank mode)
+                            }
+                        }
+                        before += __popc(kept[i]);
+                    }
+                    if (lane == 0) s.nk = min(max_det, nk + before);
+                }
+                __syncthreads();
+                nk = s.nk;
+            }
         }
         KODB_TRACE(6);
         processed += m;
@@ -861,7 +1263,7 @@ static int plan_geom(EvalGeom& g, const kodb_head_level* heads_h, const kodb_lev
     }
     (void)C;
     int rows = 0, tiles = 0;
-    const int cap = CAND_THREADS * vec;
+    const int cap = vec == 4 ? WT_CELLS : CAND_THREADS;  // warp tiles (cand_warp_kernel) / block tiles (cand_kernel<.,1>)
     for (int l = 0; l < KODB_NUM_LEVELS; ++l) {
         g.head[l] = heads_h[l];
         g.lv[l] = levels_h[l];
@@ -884,14 +1286,16 @@ static int plan_geom(EvalGeom& g, const kodb_head_level* heads_h, const kodb_lev
 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
+static size_t cand_cap(int64_t rows, int C) { return ((size_t)rows * C + 3) & ~(size_t)3; }  // float4-aligned per image
+
 static int64_t ws_bytes(int batch, int64_t rows, int C, int chunks_per_image) {
-    const size_t cap = (size_t)rows * C;
+    const size_t cap = cand_cap(rows, C);
     return (int64_t)(align256((size_t)batch * 4) + align256((size_t)batch * HB * 4) +
                      2 * align256((size_t)batch * chunks_per_image * 4) + 2 * align256((size_t)batch * cap * 4));
 }
 
 static int carve_ws(EvalParams& p, void* ws, int64_t ws_bytes_avail) {
-    const size_t cap = (size_t)p.rows * p.C;
+    const size_t cap = cand_cap(p.rows, p.C);
     if (ws_bytes_avail < ws_bytes(p.B, p.rows, p.C, p.chunks_per_image)) return KODB_ERR_CAPACITY;
     char* w = reinterpret_cast<char*>(ws);
     // the two zero-on-entry arrays sit at FIXED offsets so a cached workspace survives a geometry change
@@ -961,7 +1365,7 @@ extern "C" void kodb_debug_set_nms_trace(void* ptr) { kodb::g_trace = reinterpre
 
 extern "C" int64_t kodb_eval_workspace_bytes(int32_t batch, int64_t rows_per_image, int32_t num_classes) {
     // upper bound of chunks per image: tiles <= ceil(rows/256) + one ragged tile per (level, anchor) plane
-    const int tiles = (int)((rows_per_image + kodb::CAND_THREADS - 1) / kodb::CAND_THREADS) + KODB_NUM_LEVELS * KODB_MAX_ANCHORS;
+    const int tiles = (int)((rows_per_image + kodb::WT_CELLS - 1) / kodb::WT_CELLS) + KODB_NUM_LEVELS * KODB_MAX_ANCHORS;
     const int groups = (num_classes + kodb::CGROUP - 1) / kodb::CGROUP;
     return kodb::ws_bytes(batch, rows_per_image, num_classes, tiles * groups);
 }
@@ -995,9 +1399,16 @@ extern "C" int kodb_eval_tail(const kodb_head_level* heads_h, const kodb_level_c
     cudaStream_t st = (cudaStream_t)stream;
     const int stages = cfg_h->stage_mask ? cfg_h->stage_mask : 3;
     if (stages & 1) {
-        if (vec == 4) cand_kernel<true, 4><<<dim3(tiles, batch), CAND_THREADS, 0, st>>>(p);
-        else cand_kernel<true, 1><<<dim3(tiles, batch), CAND_THREADS, 0, st>>>(p);
-        KODB_CHECK_LAUNCH();
+        if (vec == 4) {
+            const dim3 grid((tiles + CW_WARPS - 1) / CW_WARPS, batch);
+            const int nq = p.C < CGROUP ? p.C : CGROUP;
+            rc = nq <= 4 ? launch_cand_warp<4>(p, grid, st) : nq <= 8 ? launch_cand_warp<8>(p, grid, st)
+                 : nq <= 12 ? launch_cand_warp<12>(p, grid, st) : launch_cand_warp<16>(p, grid, st);
+            if (rc != KODB_OK) return rc;
+        } else {
+            cand_kernel<true, 1><<<dim3(tiles, batch), CAND_THREADS, 0, st>>>(p);
+            KODB_CHECK_LAUNCH();
+        }
     }
     return (stages & 2) ? launch_select(p, st) : KODB_OK;
 }

@@ -57,6 +57,11 @@ __device__ __forceinline__ float rcp_approx(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+__device__ __forceinline__ float lg2_approx(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float sigmoid_eval(float x) {
     const float t = fminf(fmaxf(-x, -87.0f), 87.0f);
     return rcp_approx(1.0f + exp_fast(t));
