@@ -180,6 +180,9 @@ typedef struct kodb_match_out {
     double iou_thrs[KODB_NUM_IOU_THRS];
 } kodb_match_out;
 
+/* Eval workspace: zero-filled once after allocation; every call leaves it reusable by later calls WITH THE SAME
+ * `batch` (the zero-on-entry counters / histograms are laid out by batch size).  Re-zero it, or use another
+ * buffer, before a call with a different batch size. */
 int64_t kodb_eval_workspace_bytes(int32_t batch, int64_t rows_per_image, int32_t num_classes);
 
 /* kodb_nms: non_max_suppression(detections, conf_thres, nms_thres, classes) (kod/core/nms.py:9-75) on a

@@ -188,14 +188,19 @@ def pack_targets(targets: Sequence, device) -> PackedTargets:
 
 # ---- workspaces -----------------------------------------------------------------------------------
 _WORKSPACES: dict = {}
+_MAX_CACHED = 8
 
 
-def workspace(kind: str, device, nbytes: int) -> torch.Tensor:
-    """Zero-initialised, cached per (kind, device, stream); grown on demand.  Kernels leave workspaces
-    reusable, so the memset happens only at (re)allocation."""
-    key = (kind, torch.device(device).index, torch.cuda.current_stream(device).cuda_stream)
-    ws = _WORKSPACES.get(key)
+def workspace(kind: str, device, nbytes: int, tag=None) -> torch.Tensor:
+    """Zero-initialised, cached per (kind, device, stream, tag); grown on demand.  Kernels leave workspaces
+    reusable FOR THE SAME LAYOUT, so the memset happens only at (re)allocation.  `tag` names the layout of the
+    zero-on-entry regions (the eval workspace places them by batch size, include/kodb.h): a different tag gets a
+    different buffer instead of a stale one.  The cache keeps the most recently used few buffers."""
+    key = (kind, torch.device(device).index, torch.cuda.current_stream(device).cuda_stream, tag)
+    ws = _WORKSPACES.pop(key, None)
     if ws is None or ws.numel() < nbytes:
         ws = torch.zeros(int(nbytes), dtype=torch.uint8, device=device)
-        _WORKSPACES[key] = ws
+    _WORKSPACES[key] = ws  # (re)insert as most recent
+    while len(_WORKSPACES) > _MAX_CACHED:
+        _WORKSPACES.pop(next(iter(_WORKSPACES)))
     return ws

@@ -371,13 +371,13 @@ __global__ void __launch_bounds__(CW_WARPS * 32, 2) cand_warp_kernel(const __gri
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     constexpr unsigned CELL_MASK = (1u << NQ) - 1u;  // the NQ class bits of one cell
     float4 q[NQ];
-    const float4 xo = in_range ? __ldg(reinterpret_cast<const float4*>(obj_base + cell0)) : zero4;
+    const float4 xo = in_range ? __ldcs(reinterpret_cast<const float4*>(obj_base + cell0)) : zero4;
     {
         const int jn = min(C, CGROUP);
         const float* cp = cls_base + cell0;
 #pragma unroll
         for (int u = 0; u < NQ; ++u) {
-            q[u] = (in_range && u < jn) ? __ldg(reinterpret_cast<const float4*>(cp)) : zero4;
+            q[u] = (in_range && u < jn) ? __ldcs(reinterpret_cast<const float4*>(cp)) : zero4;
             cp += cls_step;
         }
     }
@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(CW_WARPS * 32, 2) cand_warp_kernel(const __gri
             const float* cp = cls_base + (int64_t)j0 * cls_step + cell0;
 #pragma unroll
             for (int u = 0; u < NQ; ++u) {
-                q[u] = (in_range && u < jn) ? __ldg(reinterpret_cast<const float4*>(cp)) : zero4;
+                q[u] = (in_range && u < jn) ? __ldcs(reinterpret_cast<const float4*>(cp)) : zero4;
                 cp += cls_step;
             }
         }
@@ -538,7 +538,8 @@ struct NmsSmem {
     int cprefix[CHUNK_CAP];
     unsigned long long sort_ck[K_CAP];
     float bx1[K_CAP], by1[K_CAP], bx2[K_CAP], by2[K_CAP], barea[K_CAP];      // batch, score order
-    float cx1[K_CAP], cy1[K_CAP], cx2[K_CAP], cy2[K_CAP], carea[K_CAP];      // batch, class-major order
+    float4 cbox[K_CAP];  // batch, class-major order (x1, y1, x2, y2 with the class offset)
+    float carea[K_CAP];
     unsigned pm[K_CAP * CLS_WORDS];  // pm[pos][J]: earlier same-class candidates 32J..32J+31 that suppress `pos`
     unsigned char pre[K_CAP], keepf[K_CAP];
     int ccount[KODB_MAX_CLASSES], cbase[KODB_MAX_CLASSES], tstart[KODB_MAX_CLASSES + 1];
@@ -549,10 +550,12 @@ struct NmsSmem {
     int scan_tmp[33];
     int alive[NMS_STEP];
     unsigned mask[NMS_STEP][NMS_STEP / 32];
+    int bstart[HB], bfill[HB];  // batch-relative start / fill count of every coarse bin of the current batch
     int sel_bin, sel_p, sel_prev;
     int cnt, nk, cls_over;
 };
-static_assert(sizeof(NmsSmem) + sizeof(unsigned long long) * 0 <= 200 * 1024, "NmsSmem budget");
+constexpr int RANK_CAP = 192;  // bins up to this population are ordered by counting; a heavier bin falls back to the bitonic sort
+static_assert(sizeof(NmsSmem) <= 180 * 1024, "NmsSmem budget");
 static_assert(NB >= 32 * KODB_MAX_CLASSES, "per-(warp, class) counts alias the fine histogram");
 
 __device__ __forceinline__ bool suppresses(float ax1, float ay1, float ax2, float ay2, float aarea, float bx1, float by1,
@@ -729,6 +732,8 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
     // x + offset is monotone, so disjoint stays disjoint), and a threshold >= 0 (zero overlap never suppresses).
     const float win_lo = -0.25f * max_wh, win_hi = 0.75f * max_wh;
     bool cls_static = iou_thr >= 0.0 && max_wh > 0.0f && max_wh < 3.0e38f && (double)win_hi - (double)win_lo <= (double)max_wh;
+    const float thr_rd = __double2float_rd(iou_thr);
+    const float thr_hi = thr_rd * 1.000001f, thr_lo = thr_rd * 0.999999f;  // guard band of the approximate ratio test
     cls_static = __syncthreads_and(tid >= C || (double)((float)tid * max_wh) == (double)tid * (double)max_wh) && cls_static;
     // ground truth of the image -> shared memory now; the loads overlap the whole selection / NMS phase
     int gt_n = 0;
@@ -765,6 +770,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
     while (nk < max_det && processed < limit) {
         unsigned long long hi_batch = U64MAX;
         int m = 0;
+        bool binned = false;
         if (!in_fine) {
             // ------------------------------------------------------------ cut from the coarse histogram
             if (tid == 0) s.sel_bin = -1;
@@ -772,16 +778,21 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
             int total;
             const int ex = block_excl_scan(v, s.scan_tmp, &total);  // (barriers inside order sel_bin's reset)
             if (ex < k_target && ex + v >= k_target) { s.sel_bin = tid; s.sel_p = ex + v; s.sel_prev = ex; }
+            if (tid < HB) { s.bstart[tid] = ex; s.bfill[tid] = 0; }
             __syncthreads();
             if (total == 0) break;  // nothing left
-            const int d = s.sel_bin;
+            const int d = s.sel_bin, dfirst = dnext;
             if (d < 0) { m = total; hi_batch = U64MAX; dnext = HB; }                     // fewer than k_target left: all
             else if (s.sel_p <= K_CAP) { m = s.sel_p; hi_batch = coarse_hi(d); dnext = d + 1; }
             else if (s.sel_prev > 0) { m = s.sel_prev; hi_batch = coarse_hi(d - 1); dnext = d; }
             else { in_fine = true; dnext = d; }  // bins before d are empty; d alone overflows the sort capacity
-            __syncthreads();
+            // whole-bin batch: candidates are collected straight into per-bin segments and ordered by counting
+            // (the barrier also orders the reads of sel_* above before their next reset)
+            const int heavy = __syncthreads_or(tid >= dfirst && tid < dnext && v > RANK_CAP);
+            binned = !in_fine && !heavy;
         }
         if (in_fine) {
+            binned = false;
             // ------------------------------------------------------------ radix-select inside coarse bin `dnext`
             const unsigned long long fine_hi = coarse_hi(dnext);
             unsigned long long glo = lo, ghi = fine_hi, rlo = lo;
@@ -858,7 +869,22 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
                         if (i + w < n && dk >= dlo && (open_hi || dk < dhi)) take |= 1u << (4 * u + w);
                     }
                 }
-                if (__ballot_sync(KODB_FULL_MASK, take != 0u)) {  // one shared atomic per warp and round
+                if (binned) {
+                    if (take) {  // into the candidate's own bin segment (order inside a segment is arbitrary)
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int i = 4 * (r0 + u * NMS_THREADS + tid);
+                            const float vv[4] = {sv[u].x, sv[u].y, sv[u].z, sv[u].w};
+#pragma unroll
+                            for (int w = 0; w < 4; ++w)
+                                if ((take >> (4 * u + w)) & 1u) {
+                                    const int d = coarse_bin(vv[w]);
+                                    const int pos = s.bstart[d] + atomicAdd(&s.bfill[d], 1);
+                                    s.sort_ck[pos] = ((unsigned long long)desc_key(vv[w]) << 32) | __ldg(key + i + w);
+                                }
+                        }
+                    }
+                } else if (__ballot_sync(KODB_FULL_MASK, take != 0u)) {  // one shared atomic per warp and round
                     const int mine = __popc(take);
                     const int ex = warp_excl_scan_i(mine, lane);
                     int base = 0;
@@ -883,30 +909,74 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
         }
         __syncthreads();
         KODB_TRACE(3);
-        m = s.cnt;  // == the histogram count
-        // bitonic sort, one element per thread: compare-exchange distances < 32 stay in registers (warp
-        // shuffles), larger distances go through shared memory
-        {
-            unsigned long long myk = tid < m ? s.sort_ck[tid] : U64MAX;
-            int npad = 32;
-            while (npad < m) npad <<= 1;
-            __syncthreads();
-            for (int k = 2; k <= npad; k <<= 1) {
-                for (int j = k >> 1; j > 0; j >>= 1) {
-                    unsigned long long ok;
-                    if (j >= 32) {
-                        s.sort_ck[tid] = myk;
-                        __syncthreads();
-                        ok = s.sort_ck[tid ^ j];
-                        __syncthreads();
-                    } else {
-                        ok = __shfl_xor_sync(KODB_FULL_MASK, myk, j);
-                    }
-                    const bool take_min = ((tid & j) == 0) == ((tid & k) == 0);
-                    if ((ok < myk) == take_min && ok != myk) myk = ok;
-                }
+        if (!binned) m = s.cnt;  // == the histogram count
+        if (binned) {
+            // bins are already in place (descending score = ascending bin); order every segment by counting the
+            // smaller composite keys inside it (keys are unique)
+            unsigned long long ck = 0ull;
+            int dst = 0;
+            if (tid < m) {
+                ck = s.sort_ck[tid];
+                const int d = coarse_bin(score_of_key((uint32_t)(ck >> 32)));
+                const int s0 = s.bstart[d], s1 = s0 + s.chist[d];
+                int r = 0;
+                for (int q = s0; q < s1; ++q) r += s.sort_ck[q] < ck;
+                dst = s0 + r;
             }
-            s.sort_ck[tid] = myk;
+            __syncthreads();
+            if (tid < m) s.sort_ck[dst] = ck;
+            __syncthreads();
+        } else
+        // bitonic sort, FOUR elements per thread (element i = 4t + r) on the first npad/4 threads only: distances
+        // 1, 2 are exchanges inside the thread, 4..64 warp shuffles, >= 128 go through shared memory behind a named
+        // barrier of just the participating warps (3 such stages for 512 elements, instead of 10 block barriers)
+        {
+            int npad = 128;
+            while (npad < m) npad <<= 1;
+            const int nthr = npad >> 2;
+            if (tid < nthr) {
+                unsigned long long v[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) v[r] = 4 * tid + r < m ? s.sort_ck[4 * tid + r] : U64MAX;
+                for (int k = 2; k <= npad; k <<= 1) {
+                    for (int j = k >> 1; j > 0; j >>= 1) {
+                        if (j >= 4) {
+                            const int jt = j >> 2;  // partner thread distance
+                            unsigned long long o[4];
+                            if (jt >= 32) {
+#pragma unroll
+                                for (int r = 0; r < 4; ++r) s.sort_ck[4 * tid + r] = v[r];
+                                asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
+#pragma unroll
+                                for (int r = 0; r < 4; ++r) o[r] = s.sort_ck[4 * (tid ^ jt) + r];
+                                asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
+                            } else {
+#pragma unroll
+                                for (int r = 0; r < 4; ++r) o[r] = __shfl_xor_sync(KODB_FULL_MASK, v[r], jt);
+                            }
+                            const bool lower = (tid & jt) == 0;
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) {
+                                const bool asc = ((4 * tid + r) & k) == 0;
+                                if ((o[r] < v[r]) == (lower == asc) && o[r] != v[r]) v[r] = o[r];
+                            }
+                        } else {
+                            // partner inside the thread: r ^ j (compile-time register indices)
+                            if (j == 2) {
+                                const bool a0 = ((4 * tid) & k) == 0;  // elements 0..3 share bit k for k >= 4; k == 2 never has j == 2
+                                if ((v[0] > v[2]) == a0) { const unsigned long long x = v[0]; v[0] = v[2]; v[2] = x; }
+                                if ((v[1] > v[3]) == a0) { const unsigned long long x = v[1]; v[1] = v[3]; v[3] = x; }
+                            } else {
+                                const bool a0 = ((4 * tid) & k) == 0, a2 = ((4 * tid + 2) & k) == 0;
+                                if ((v[0] > v[1]) == a0) { const unsigned long long x = v[0]; v[0] = v[1]; v[1] = x; }
+                                if ((v[2] > v[3]) == a2) { const unsigned long long x = v[2]; v[2] = v[3]; v[3] = x; }
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) s.sort_ck[4 * tid + r] = v[r];
+            }
             __syncthreads();
         }
         KODB_TRACE(4);
@@ -973,18 +1043,21 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
                 if (lane == 0) { s.tstart[C] = run_t; s.cls_over = over; }
             }
             __syncthreads();
+            KODB_TRACE(10);
             cls_path = !s.cls_over;
             if (cls_path) {
                 if (my_c >= 0) {
                     my_pos = s.cbase[my_c] + s.hist[wid * C + my_c] + rank;
                     const float x1 = s.bx1[tid], y1 = s.by1[tid], x2 = s.bx2[tid], y2 = s.by2[tid], ar = s.barea[tid];
-                    s.cx1[my_pos] = x1; s.cy1[my_pos] = y1; s.cx2[my_pos] = x2; s.cy2[my_pos] = y2; s.carea[my_pos] = ar;
+                    s.cbox[my_pos] = make_float4(x1, y1, x2, y2);
+                    s.carea[my_pos] = ar;
                     bool dead = false;  // suppressed by a survivor of an earlier batch (same class only)
                     for (int q = 0; q < nk && !dead; ++q)
                         dead = s.kcls[q] == my_c && suppresses(s.kx1[q], s.ky1[q], s.kx2[q], s.ky2[q], s.karea[q], x1, y1, x2, y2, ar, iou_thr);
                     s.pre[my_pos] = dead;
                 }
                 __syncthreads();
+                KODB_TRACE(11);
                 const int T = s.tstart[C];
                 for (int tt = wid; tt < T; tt += NMS_THREADS / 32) {
                     int c = 0;
@@ -1003,18 +1076,32 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
                     const int i = 32 * I + lane;
                     const bool vi = i < nc;
                     const int pi = base + (vi ? i : 0);
-                    const float i1 = s.cx1[pi], i2 = s.cy1[pi], i3 = s.cx2[pi], i4 = s.cy2[pi], ia = s.carea[pi];
+                    const float4 bi = s.cbox[pi];
+                    const float ia = s.carea[pi];
                     const int jend = min(32, min(nc, 32 * I + 31) - 32 * J);  // j < i <= 32I+31
+                    // Branch-free, unrolled: the iterations are independent, so their latency chains overlap.
+                    // (double)ovr > thr  <=>  ovr > thr_rd (thr rounded DOWN to fp32).  The IEEE division is only
+                    // executed when the approximate ratio is within 1e-6 (relative) of the threshold.
                     unsigned word = 0u;
+                    const int pj0 = base + 32 * J;
+#pragma unroll 4
                     for (int jj = 0; jj < jend; ++jj) {
-                        const int pj = base + 32 * J + jj;
-                        const bool hit = vi && (32 * J + jj < i) &&
-                                         suppresses(s.cx1[pj], s.cy1[pj], s.cx2[pj], s.cy2[pj], s.carea[pj], i1, i2, i3, i4, ia, iou_thr);
+                        const float4 bj = s.cbox[pj0 + jj];
+                        const float xx1 = fmaxf(bj.x, bi.x), yy1 = fmaxf(bj.y, bi.y);
+                        const float xx2 = fminf(bj.z, bi.z), yy2 = fminf(bj.w, bi.w);
+                        const float w = fmaxf(0.0f, xx2 - xx1), h = fmaxf(0.0f, yy2 - yy1);
+                        const float inter = w * h;
+                        const float den = s.carea[pj0 + jj] + ia - inter;
+                        const float qa = inter * rcp_approx(den);
+                        bool hit = qa > thr_hi;
+                        if (!hit && !(qa < thr_lo)) hit = inter / den > thr_rd;  // rare (also NaN / degenerate boxes)
                         word |= (unsigned)hit << jj;
                     }
+                    if (I == J) word &= (1u << lane) - 1u;  // diagonal tile: only earlier candidates
                     if (vi) s.pm[(size_t)pi * CLS_WORDS + J] = word;
                 }
                 __syncthreads();
+                KODB_TRACE(12);
                 for (int c = wid; c < C; c += NMS_THREADS / 32) {
                     const int nc = s.ccount[c];
                     if (nc == 0) continue;
@@ -1044,6 +1131,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
                     }
                 }
                 __syncthreads();
+                KODB_TRACE(13);
                 const int kf = (my_c >= 0 && s.keepf[my_pos]) ? 1 : 0;
                 int tot;
                 const int ex = block_excl_scan(kf, s.scan_tmp, &tot);

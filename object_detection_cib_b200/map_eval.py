@@ -102,7 +102,7 @@ class DeviceCocoMapEvaluator(object):
         lib = L.lib()
         n_img = int(counts.shape[0])
         ap = torch.empty((L.NUM_IOU_THRS, self.num_classes), dtype=torch.float64, device=dev)
-        ws = H.workspace("ap", dev, lib.kodb_ap_workspace_bytes(n_img, self.max_det, self.num_classes))
+        ws = H.workspace("ap", dev, lib.kodb_ap_workspace_bytes(n_img, self.max_det, self.num_classes), tag=self.num_classes)
         L.check(lib.kodb_ap_accumulate(score.data_ptr(), cls.data_ptr(), tp.data_ptr(), counts.data_ptr(), n_img,
                                        self.max_det, self.num_classes, gt_count.data_ptr(), ap.data_ptr(),
                                        ws.data_ptr(), ws.numel(), H.stream_ptr(dev)), "kodb_ap_accumulate")

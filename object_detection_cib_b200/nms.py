@@ -114,7 +114,7 @@ def nms_padded(detections: torch.Tensor, conf_thres: float = 0.25, nms_thres: fl
     lib = L.lib()
     cfg = _nms_cfg(C, conf_thres, nms_thres, classes, max_det, max_nms)
     res, out = _alloc_out(B, max_det, dev)
-    ws = H.workspace("eval", dev, lib.kodb_eval_workspace_bytes(B, N, C))
+    ws = H.workspace("eval", dev, lib.kodb_eval_workspace_bytes(B, N, C), tag=B)
     packed, match = None, None
     if targets is not None:
         packed = targets if isinstance(targets, H.PackedTargets) else H.pack_targets(targets, dev)
@@ -136,7 +136,7 @@ def eval_tail(image_feature_shape: FeatureShape, net_result, anchor_info, conf_t
     rows = sum(lv.num_anchors * lv.H * lv.W for lv in levels)
     cfg = _nms_cfg(heads.num_classes, conf_thres, nms_thres, classes, max_det, max_nms)
     res, out = _alloc_out(heads.batch, max_det, dev)
-    ws = H.workspace("eval", dev, lib.kodb_eval_workspace_bytes(heads.batch, rows, heads.num_classes))
+    ws = H.workspace("eval", dev, lib.kodb_eval_workspace_bytes(heads.batch, rows, heads.num_classes), tag=heads.batch)
     packed, match = None, None
     if targets is not None:
         packed = targets if isinstance(targets, H.PackedTargets) else H.pack_targets(targets, dev)
