@@ -66,6 +66,14 @@ struct EvalParams {
     int* chunk_start;  // [B][chunks_per_image]
     int* chunk_count;  // [B][chunks_per_image]
     int tiles_per_image, chunks_per_image;
+    // floor mode (planar float4 path): only candidates at or above a per-image score floor are listed; every
+    // candidate is recorded as a bit in `mask` (keep indices, the rare completion pass)
+    int floor_mode;
+    int ns, sample_stride;     // sample tiles per image: tiles 0, S, 2S, ... (one per warp of the image's sample CTA)
+    int hot_target;            // estimated number of listed candidates per image the floor aims at
+    int* floor_word;           // [B]  (floor bin + 1), 0 = not published yet; zero on entry / exit
+    unsigned short* mask;      // [B][ngroups][rows]  bit u: class 16*group + u of the row is a candidate
+    int64_t mask_stride;       // elements per image
     kodb_nms_out out;
     // matching
     int do_match;
@@ -340,25 +348,79 @@ __device__ __forceinline__ unsigned long long expand_nibbles(unsigned a16) {  //
     return x * 15ull;
 }
 
-template <int NQ>
-struct CandWarpSmem {  // one per warp: the kernel has no block-level barrier
-    float q[NQ][WT_CELLS];               // class logits of the tile (stash: candidates are re-read by id)
-    float o[WT_CELLS];                   // sigmoid(obj) per cell
-    unsigned hist[HB / 2];               // two 16-bit bins per word
-    unsigned short list[WT_CELLS * NQ];  // flagged (cell, class) ids
-};
+constexpr int HOT_TARGET = 2048;
+
+// smallest positive score of coarse bin d (d < HB - 1)
+__device__ __forceinline__ float coarse_lower_edge(int d) { return __uint_as_float(((0x3F800000u >> 18) - (uint32_t)d) << 18); }
 
 template <int NQ>
-__global__ void __launch_bounds__(CW_WARPS * 32, 2) cand_warp_kernel(const __grid_constant__ EvalParams p) {
+struct CandWarpSmem {  // one per warp: the data path of the kernel has no block-level barrier
+    float q[NQ][WT_CELLS];               // class logits of the tile (stash: candidates are re-read by id)
+    float o[WT_CELLS];                   // sigmoid(obj) per cell
+    unsigned short list[WT_CELLS * NQ];  // ids of the (cell, class) pairs to list
+};
+
+// Candidate kernel of the fused path.  One WARP owns a tile of up to 128 contiguous cells of one (level, anchor)
+// plane: lane l holds cells 4l..4l+3.  No block-level barrier, no waiting on other CTAs.
+//  * Every global load of the tile (the obj float4 and the NQ class float4s of the lane, evict-first) is issued
+//    before the first use: one DRAM round trip per tile.
+//  * The per-pair decision is one subtraction whose sign bit is funnel-shifted into a mask:
+//    sigmoid(q)*o > thr  <=>  q > tau(o) = logit(thr/o) in exact arithmetic; pairs with |q - tau| <= TAU_WINDOW (a
+//    few per thousand) are re-decided with the decode kernel's exact fp32 product, so the candidate set is the one
+//    kodb_decode + kodb_nms would produce.  The set is stored as one 16-bit class mask per cell.
+//  * Only the candidates that can matter for the first max_det survivors are LISTED (score, key): those whose
+//    score reaches a per-image floor.  The floor is measured, not guessed: the sample tiles (every 16th tile, the
+//    lowest block indices, so they run first) list all their candidates and feed a sample histogram; the warp
+//    finishing the image's last sample tile picks the histogram bin above which an estimated hot_target
+//    candidates lie and publishes it.  A tile that finds the floor published lists only the pairs whose score
+//    bin reaches it (a second sign mask against logit(floor/o)); a tile that comes too early lists everything, like
+//    a sample tile, and says so in its tile flag.  The select kernel completes the list from the masks in the rare
+//    case it runs dry.  Results never depend on the floor or on timing; only the amount of listing work does.
+template <int NQ>
+__device__ __forceinline__ unsigned fix_borderline(unsigned cmv, unsigned border, const float (*sq)[WT_CELLS], int cell, float ov,
+                                                    float thr, int floor_bin) {
+    while (border) {
+        const int u = __ffs(border) - 1;
+        border &= border - 1;
+        cmv &= ~(1u << u);
+        const float conf = sigmoid_eval(sq[u][cell]) * ov;  // the decode kernel's arithmetic
+        if (ov > thr && conf > thr && coarse_bin(conf) <= floor_bin) cmv |= 1u << u;
+    }
+    return cmv;
+}
+
+template <int NQ>
+__global__ void __launch_bounds__(CW_WARPS * 32, 3) cand_floor_kernel(const __grid_constant__ EvalParams p) {
     extern __shared__ __align__(16) unsigned char cw_smem_raw[];
-    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     CandWarpSmem<NQ>& sm = reinterpret_cast<CandWarpSmem<NQ>*>(cw_smem_raw)[wid];
-    const int t = blockIdx.x * CW_WARPS + wid;
-    if (t >= p.tiles_per_image) return;
+    // work order: CTA b < B is image b's sample CTA (one sample tile per warp, tiles 0, S, 2S, ...; it runs first and
+    // keeps the sample histogram in shared memory); the other CTAs take the remaining tiles, image index fastest, so
+    // that neighbouring warps work on different images and the per-image atomics do not pile up on one address
+    __shared__ int s_shist[HB];
+    const int T = p.tiles_per_image, S = p.sample_stride, ns = p.ns, nr = T - ns, B = p.B;
+    const bool sample = (int)blockIdx.x < B;
+    int b, t;
+    bool active = true;
+    if (sample) {
+        b = blockIdx.x;
+        t = wid * S;
+        active = wid < ns;
+        for (int i = tid; i < HB; i += CW_WARPS * 32) s_shist[i] = 0;
+        __syncthreads();
+    } else {
+        const int g2 = ((int)blockIdx.x - B) * CW_WARPS + wid;
+        if (g2 >= nr * B) return;
+        const int ri = g2 / B;
+        b = g2 - ri * B;
+        t = ri + ri / (S - 1) + 1;  // ri-th tile index that is not a multiple of S (S >= 2 whenever nr > 0)
+    }
+    if (!active) {  // idle warp of a sample CTA: only the block barrier in front of the floor computation
+        __syncthreads();
+        return;
+    }
     const int C = p.C;
     const float thr = p.cfg.conf_thres;
-#pragma unroll
-    for (int i = 0; i < HB / 64; ++i) sm.hist[32 * i + lane] = 0u;
     int L, a, c0, ncell;
     planar_tile(p.g, t, L, a, c0, ncell);
     const kodb_head_level& hd = p.g.head[L];
@@ -370,21 +432,50 @@ __global__ void __launch_bounds__(CW_WARPS * 32, 2) cand_warp_kernel(const __gri
     const bool in_range = cell0 < ncell;  // tiles are multiples of 4 cells
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     constexpr unsigned CELL_MASK = (1u << NQ) - 1u;  // the NQ class bits of one cell
-    float4 q[NQ];
-    const float4 xo = in_range ? __ldcs(reinterpret_cast<const float4*>(obj_base + cell0)) : zero4;
+    // Asynchronous 16-byte copies global -> the warp's shared stash (LDGSTS): all of the tile's bytes are in flight
+    // at once without holding registers, so three CTAs fit on an SM.  The obj logits land in sm.o and are replaced
+    // by their sigmoid below.
+    if (in_range) cp_async16(&sm.o[cell0], obj_base + cell0);
+    else *reinterpret_cast<float4*>(&sm.o[cell0]) = zero4;
     {
         const int jn = min(C, CGROUP);
         const float* cp = cls_base + cell0;
 #pragma unroll
         for (int u = 0; u < NQ; ++u) {
-            q[u] = (in_range && u < jn) ? __ldcs(reinterpret_cast<const float4*>(cp)) : zero4;
+            if (in_range && u < jn) cp_async16(&sm.q[u][cell0], cp);
+            else *reinterpret_cast<float4*>(&sm.q[u][cell0]) = zero4;
             cp += cls_step;
         }
     }
-    // per cell: objectness, row filter (nms.py:33) and the class-logit threshold (branch-free)
-    float tau[4];
-    unsigned force = 0u;  // cells whose passing pairs all take the exact test
+    cp_async_commit();
+    // the image's floor, if its sample CTA is through already (the read overlaps the copies above)
+    int floor_bin = HB - 1;  // HB - 1: list everything
+    if (!sample) {
+        const int w = *(const volatile int*)(p.floor_word + b);
+        if (w > 0) floor_bin = w - 1;
+    }
+    bool full = floor_bin >= HB - 1;
+    // per cell: objectness, row filter (nms.py:33), the class-logit threshold of the candidate test and the one of
+    // the floor test (branch-free)
+    float tau[4], tauf[4], oa[4];  // oa: objectness of an active cell, -1 otherwise
+    unsigned force = 0u, forcef = 0u;  // cells whose passing pairs all take the exact test
+    // floor test: score = sigmoid(q) * o reaches the floor's lower edge fl only if o >= fl; same construction as the
+    // candidate test with fl in place of thr
+    auto floor_cells = [&]() {
+        const float fl = coarse_lower_edge(floor_bin);
+        forcef = 0u;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const float rf = fl * rcp_approx(oa[v]);
+            const bool richc = oa[v] >= fl, fastf = richc && rf < 0.9f;
+            const float tf = 0.693147182464599609375f * lg2_approx(rf * rcp_approx(1.0f - rf));
+            tauf[v] = richc ? (fastf ? tf : 2.19f) : 3.0e38f;
+            if (richc && !fastf) forcef |= 1u << v;
+        }
+    };
+    cp_async_wait_all();  // every lane reads back only what it copied itself until the __syncwarp further down
     {
+        const float4 xo = *reinterpret_cast<const float4*>(&sm.o[cell0]);
         const float x[4] = {xo.x, xo.y, xo.z, xo.w};
         float ov4[4];
 #pragma unroll
@@ -392,6 +483,7 @@ __global__ void __launch_bounds__(CW_WARPS * 32, 2) cand_warp_kernel(const __gri
             const float ov = sigmoid_eval(x[v]);
             ov4[v] = ov;
             const bool act = in_range && ov > thr;
+            oa[v] = act ? ov : -1.0f;
             const float r = thr * rcp_approx(ov);  // thr / o, in (0, 1) for an active cell
             const bool fast = act && thr > 0.0f && r < 0.9f;
             const float tv = 0.693147182464599609375f * lg2_approx(r * rcp_approx(1.0f - r));  // logit(thr / o)
@@ -399,42 +491,66 @@ __global__ void __launch_bounds__(CW_WARPS * 32, 2) cand_warp_kernel(const __gri
             // 2.19 is a safe lower bound -- the (very few) pairs above it are re-decided exactly.  thr <= 0: all are.
             const float slow_tau = thr > 0.0f ? 2.19f : -3.0e38f;
             tau[v] = act ? (fast ? tv : slow_tau) : 3.0e38f;  // inactive cell: nothing passes
+            tauf[v] = 3.0e38f;
             if (act && !fast) force |= 1u << v;
         }
         *reinterpret_cast<float4*>(&sm.o[cell0]) = make_float4(ov4[0], ov4[1], ov4[2], ov4[3]);
     }
+    if (!full) floor_cells();
     float* sc_img = p.cand_score + (int64_t)b * p.cand_stride;
     uint32_t* ky_img = p.cand_key + (int64_t)b * p.cand_stride;
+    int* hist_img = p.hist + (int64_t)b * HB;
     for (int grp = 0; grp < p.ngroups; ++grp) {
         const int j0 = grp * CGROUP, jn = min(C - j0, CGROUP);
         if (grp > 0) {
+            __syncwarp();  // the previous group's readers of the stash are done
             const float* cp = cls_base + (int64_t)j0 * cls_step + cell0;
 #pragma unroll
             for (int u = 0; u < NQ; ++u) {
-                q[u] = (in_range && u < jn) ? __ldcs(reinterpret_cast<const float4*>(cp)) : zero4;
+                if (in_range && u < jn) cp_async16(&sm.q[u][cell0], cp);
+                else *reinterpret_cast<float4*>(&sm.q[u][cell0]) = zero4;
                 cp += cls_step;
             }
+            cp_async_commit();
+            cp_async_wait_all();
         }
         // pair (u, v): the sign bit of (tau[v] - q[u][v]) is funnel-shifted into one mask per cell (four
-        // independent dependency chains); class u ends at bit NQ-1-u of the chain
-        unsigned mv[4] = {0u, 0u, 0u, 0u};
-        float amin = 3.0e38f;
+        // independent dependency chains); class u ends at bit NQ-1-u of the chain.  Same for the floor test.
+        unsigned mv[4] = {0u, 0u, 0u, 0u}, mf[4] = {0u, 0u, 0u, 0u};
+        float amin = 3.0e38f, aminf = 3.0e38f;
+        if (full) {
 #pragma unroll
-        for (int u = 0; u < NQ; ++u) {
-            *reinterpret_cast<float4*>(&sm.q[u][cell0]) = q[u];
-            const float qq[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+            for (int u = 0; u < NQ; ++u) {
+                const float4 q4 = *reinterpret_cast<const float4*>(&sm.q[u][cell0]);
+                const float qq[4] = {q4.x, q4.y, q4.z, q4.w};
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                const float d = tau[v] - qq[v];
-                mv[v] = __funnelshift_l(__float_as_uint(d), mv[v], 1);
-                amin = fminf(amin, fabsf(d));
+                for (int v = 0; v < 4; ++v) {
+                    const float d = tau[v] - qq[v];
+                    mv[v] = __funnelshift_l(__float_as_uint(d), mv[v], 1);
+                    amin = fminf(amin, fabsf(d));
+                }
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < NQ; ++u) {
+                const float4 q4 = *reinterpret_cast<const float4*>(&sm.q[u][cell0]);
+                const float qq[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const float d = tau[v] - qq[v], df = tauf[v] - qq[v];
+                    mv[v] = __funnelshift_l(__float_as_uint(d), mv[v], 1);
+                    mf[v] = __funnelshift_l(__float_as_uint(df), mf[v], 1);
+                    amin = fminf(amin, fabsf(d));
+                    aminf = fminf(aminf, fabsf(df));
+                }
             }
         }
-        unsigned cm[4];  // cm[v] bit u: pair (class j0+u, cell cell0+v) is a candidate
+        unsigned cm[4], hm[4];  // bit u: pair (class j0+u, cell cell0+v) is a candidate / reaches the floor
         unsigned fany = 0u;
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
             cm[v] = __brev(mv[v]) >> (32 - NQ);
+            hm[v] = __brev(mf[v]) >> (32 - NQ);
             if ((force >> v) & 1u) fany |= cm[v];
         }
         if (amin <= TAU_WINDOW || fany) {  // rare: re-decide the borderline pairs with the decode kernel's arithmetic
@@ -442,16 +558,9 @@ __global__ void __launch_bounds__(CW_WARPS * 32, 2) cand_warp_kernel(const __gri
             for (int v = 0; v < 4; ++v) {
                 unsigned border = ((force >> v) & 1u) ? cm[v] : 0u;  // forced cell: every pair above the conservative bound
 #pragma unroll
-                for (int u = 0; u < NQ; ++u) {
+                for (int u = 0; u < NQ; ++u)
                     if (fabsf(tau[v] - sm.q[u][cell0 + v]) <= TAU_WINDOW) border |= 1u << u;  // (own stash: no sync needed)
-                }
-                const float ov = sm.o[cell0 + v];
-                while (border) {
-                    const int u = __ffs(border) - 1;
-                    border &= border - 1;
-                    cm[v] &= ~(1u << u);
-                    if (ov > thr && sigmoid_eval(sm.q[u][cell0 + v]) * ov > thr) cm[v] |= 1u << u;
-                }
+                if (border) cm[v] = fix_borderline<NQ>(cm[v], border, sm.q, cell0 + v, oa[v], thr, HB - 1);
             }
         }
         // classes beyond the group's end and the `classes` filter (nms.py:54-55)
@@ -462,9 +571,63 @@ __global__ void __launch_bounds__(CW_WARPS * 32, 2) cand_warp_kernel(const __gri
             cm[v] &= am;
             mine += __popc(cm[v]);
         }
-        int slot = warp_excl_scan_i(mine, lane);
-        const int n = __shfl_sync(KODB_FULL_MASK, slot + mine, 31);
-        {  // fully predicated (no per-lane loops: the lanes' candidate counts differ by 2x and more)
+        const int n_pass = warp_sum_i(mine);
+        if (in_range)  // the candidate set of the tile: one class mask per cell
+            *reinterpret_cast<uint2*>(p.mask + (int64_t)b * p.mask_stride + (int64_t)grp * p.rows + row0 + cell0) =
+                make_uint2(cm[0] | (cm[1] << 16), cm[2] | (cm[3] << 16));
+        if (full && !sample) {
+            // second chance: the floor may have been published while this tile was streaming
+            const int w = *(const volatile int*)(p.floor_word + b);
+            if (w > 0 && w - 1 < HB - 1) {
+                floor_bin = w - 1;
+                full = false;
+                floor_cells();
+#pragma unroll
+                for (int u = 0; u < NQ; ++u) {
+                    const float4 q4 = *reinterpret_cast<const float4*>(&sm.q[u][cell0]);
+                    const float qq[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        const float df = tauf[v] - qq[v];
+                        mf[v] = __funnelshift_l(__float_as_uint(df), mf[v], 1);
+                        aminf = fminf(aminf, fabsf(df));
+                    }
+                }
+#pragma unroll
+                for (int v = 0; v < 4; ++v) hm[v] = __brev(mf[v]) >> (32 - NQ);
+            }
+        }
+        if (!full) {
+            unsigned fanyf = 0u;
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+                if ((forcef >> v) & 1u) fanyf |= hm[v];
+            if (aminf <= TAU_WINDOW || fanyf) {
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    unsigned borderf = ((forcef >> v) & 1u) ? hm[v] : 0u;
+#pragma unroll
+                    for (int u = 0; u < NQ; ++u)
+                        if (fabsf(tauf[v] - sm.q[u][cell0 + v]) <= TAU_WINDOW) borderf |= 1u << u;
+                    if (borderf) hm[v] = fix_borderline<NQ>(hm[v], borderf, sm.q, cell0 + v, oa[v], thr, floor_bin);
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < 4; ++v) hm[v] &= cm[v];
+        }
+        if (lane == 0) {
+            const int64_t chunk = (int64_t)b * p.chunks_per_image + (int64_t)t * p.ngroups + grp;
+            p.chunk_count[chunk] = n_pass;
+            p.chunk_start[chunk] = full ? 1 : 0;  // chunk flag: listed in full
+        }
+        // pairs to list; the space is claimed now and the reply of the atomic is only needed after the id list is built
+        const int hot = __popc(hm[0]) + __popc(hm[1]) + __popc(hm[2]) + __popc(hm[3]);
+        const int n = full ? n_pass : warp_sum_i(hot);
+        int base = 0;
+        if (lane == 0 && n) base = atomicAdd(&p.img_count[b], n);
+        if (full) {
+            // all candidates of the tile; fully predicated (the lanes' counts differ by 2x and more)
+            const int slot = warp_excl_scan_i(mine, lane);
             unsigned short* lp = sm.list + slot;
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
@@ -473,16 +636,60 @@ __global__ void __launch_bounds__(CW_WARPS * 32, 2) cand_warp_kernel(const __gri
                 for (int u = 0; u < NQ; ++u)
                     if (cm[v] & (1u << u)) *lp++ = (unsigned short)(idb | u);
             }
+        } else {
+            // the few pairs that reach the floor
+            int slot = warp_excl_scan_i(hot, lane);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                unsigned m = hm[v];
+                while (m) {
+                    const int u = __ffs(m) - 1;
+                    m &= m - 1;
+                    sm.list[slot++] = (unsigned short)(((cell0 + v) << 4) | u);
+                }
+            }
         }
-        int base = 0;
-        if (lane == 0) {
-            const int64_t chunk = (int64_t)b * p.chunks_per_image + (int64_t)t * p.ngroups + grp;
-            base = n ? atomicAdd(&p.img_count[b], n) : 0;
-            p.chunk_start[chunk] = base;
-            p.chunk_count[chunk] = n;
+        __syncwarp();  // list, q stash and o are visible to the whole warp
+        if (sample) {
+            // sample tile: the histograms first, so that the floor is out as early as possible
+#pragma unroll 1
+            for (int i0 = 0; i0 < n; i0 += 32) {
+                const int i = i0 + lane;
+                if (i < n) {
+                    const int pid = sm.list[i];
+                    const int bin = coarse_bin(sigmoid_eval(sm.q[pid & 15][pid >> 4]) * sm.o[pid >> 4]);
+                    atomicAdd(hist_img + bin, 1);
+                    atomicAdd(&s_shist[bin], 1);
+                }
+            }
+            if (grp == p.ngroups - 1) {
+                __syncthreads();  // all sample tiles of the image are in the shared histogram
+                if (wid == 0) {
+                    // sample counts scale by T / ns to the whole image; first bin whose cumulative estimate reaches
+                    // the target (bins are in descending score order)
+                    const long long need = ((long long)p.hot_target * ns + T - 1) / T;
+                    int part = 0;
+                    int hv[HB / 32];
+#pragma unroll
+                    for (int i = 0; i < HB / 32; ++i) {
+                        hv[i] = s_shist[lane * (HB / 32) + i];
+                        part += hv[i];
+                    }
+                    int cum = warp_excl_scan_i(part, lane);
+                    int found = HB;
+#pragma unroll
+                    for (int i = 0; i < HB / 32; ++i) {
+                        cum += hv[i];
+                        if (found == HB && cum >= need) found = lane * (HB / 32) + i;
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) found = min(found, __shfl_xor_sync(KODB_FULL_MASK, found, o));
+                    const int fb = found >= HB - 1 ? HB - 1 : found;
+                    if (lane == 0) atomicExch(&p.floor_word[b], fb + 1);
+                }
+            }
         }
         base = __shfl_sync(KODB_FULL_MASK, base, 0);
-        __syncwarp();  // list, q stash and o are visible to the whole warp
         float* scp = sc_img + base;
         uint32_t* kyp = ky_img + base;
         const uint32_t key0 = (uint32_t)row0 * (uint32_t)C + (uint32_t)j0;
@@ -495,18 +702,9 @@ __global__ void __launch_bounds__(CW_WARPS * 32, 2) cand_warp_kernel(const __gri
                 const float conf = sigmoid_eval(sm.q[u][cl]) * sm.o[cl];  // the decode kernel's arithmetic
                 scp[i] = conf;
                 kyp[i] = key0 + (uint32_t)cl * (uint32_t)C + (uint32_t)u;
-                const int bin = coarse_bin(conf);  // a warp adds < 65536 candidates: the 16-bit halves cannot overflow
-                atomicAdd(&sm.hist[bin >> 1], 1u << ((bin & 1) << 4));
+                if (!sample) atomicAdd(hist_img + coarse_bin(conf), 1);
             }
         }
-        __syncwarp();
-    }
-#pragma unroll
-    for (int i = 0; i < HB / 64; ++i) {
-        const unsigned v = sm.hist[32 * i + lane];
-        int* gh = p.hist + (int64_t)b * HB + 2 * (32 * i + lane);
-        if (v & 0xffffu) atomicAdd(gh, (int)(v & 0xffffu));
-        if (v >> 16) atomicAdd(gh + 1, (int)(v >> 16));
     }
 }
 
@@ -517,11 +715,11 @@ static int launch_cand_warp(const EvalParams& p, dim3 grid, cudaStream_t st) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        if (cudaFuncSetAttribute(cand_warp_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(cand_floor_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return KODB_ERR_LAUNCH;
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    cand_warp_kernel<NQ><<<grid, CW_WARPS * 32, smem, st>>>(p);
+    cand_floor_kernel<NQ><<<grid, CW_WARPS * 32, smem, st>>>(p);
     KODB_CHECK_LAUNCH();
     return KODB_OK;
 }
@@ -705,6 +903,96 @@ __device__ void match_image(MatchSmem& ms, GtSmem& gs, int nk, int C, int ng, co
     }
 }
 
+// Floor mode, rare: the listed candidates ran dry before max_det survivors.  Lists every candidate of the image
+// that the candidate kernel left out (pairs of tiles not listed in full whose score lies in a bin below the floor), straight
+// from the class masks and the head logits, appends them to the image's list and completes the histogram.
+// Eight warps, one tile at a time each; scratch on top of the batch arrays (free between batches).  Block-wide.
+__device__ unsigned int g_completions = 0u;  // debug statistic: completion passes since the last query
+
+__device__ int complete_list(const EvalParams& p, NmsSmem& s, int b, int n0, int floor_bin) {
+    constexpr int CL_WARPS = 8;
+    if (threadIdx.x == 0) atomicAdd(&g_completions, 1u);
+    static_assert(sizeof(s.pm) >= CL_WARPS * WT_CELLS * CGROUP * sizeof(unsigned short), "id lists fit in pm");
+    static_assert(sizeof(s.bx1) >= CL_WARPS * WT_CELLS * sizeof(float), "objectness fits in bx1");
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int C = p.C;
+    if (tid == 0) s.cnt = 0;
+    __syncthreads();
+    if (wid < CL_WARPS) {
+        unsigned short* list = reinterpret_cast<unsigned short*>(s.pm) + wid * (WT_CELLS * CGROUP);
+        float* so = s.bx1 + wid * WT_CELLS;
+        float* sc_img = p.cand_score + (int64_t)b * p.cand_stride + n0;
+        uint32_t* ky_img = p.cand_key + (int64_t)b * p.cand_stride + n0;
+        const unsigned short* mask_img = p.mask + (int64_t)b * p.mask_stride;
+        for (int t = wid; t < p.tiles_per_image; t += CL_WARPS) {
+            const int* flags = p.chunk_start + (int64_t)b * p.chunks_per_image + (int64_t)t * p.ngroups;
+            int L, a, c0, ncell;
+            planar_tile(p.g, t, L, a, c0, ncell);
+            const kodb_head_level& hd = p.g.head[L];
+            const int row0 = p.g.row_base[L] + a * (p.g.lv[L].H * p.g.lv[L].W) + c0;
+            const float* obj_base = hd.obj + (int64_t)b * hd.obj_sb + (int64_t)a * hd.obj_sa + c0;
+            const float* cls_base = hd.cls + (int64_t)b * hd.cls_sb + (int64_t)a * hd.cls_sa + c0;
+            for (int i = lane; i < ncell; i += 32) so[i] = sigmoid_eval(obj_base[i]);
+            for (int g = 0; g < p.ngroups; ++g) {
+                if (flags[g]) continue;  // this chunk is listed in full already
+                const int j0 = g * CGROUP;
+                const unsigned short* mk = mask_img + (int64_t)g * p.rows + row0;
+                int mine = 0;
+                unsigned m4[4];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const int cl = 4 * lane + v;
+                    m4[v] = cl < ncell ? mk[cl] : 0u;
+                    mine += __popc(m4[v]);
+                }
+                int slot = warp_excl_scan_i(mine, lane);
+                const int n = __shfl_sync(KODB_FULL_MASK, slot + mine, 31);
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    unsigned m = m4[v];
+                    while (m) {
+                        const int u = __ffs(m) - 1;
+                        m &= m - 1;
+                        list[slot++] = (unsigned short)(((4 * lane + v) << 4) | u);
+                    }
+                }
+                __syncwarp();
+                for (int i0 = 0; i0 < n; i0 += 32) {
+                    const int i = i0 + lane;
+                    bool cold = false;
+                    float conf = 0.0f;
+                    uint32_t k32 = 0u;
+                    int bin = 0;
+                    if (i < n) {
+                        const int pid = list[i];
+                        const int cl = pid >> 4, u = pid & 15;
+                        conf = sigmoid_eval(cls_base[(int64_t)(j0 + u) * hd.cls_sp + cl]) * so[cl];  // the decode kernel's arithmetic
+                        bin = coarse_bin(conf);
+                        cold = bin > floor_bin;
+                        k32 = (uint32_t)(row0 + cl) * (uint32_t)C + (uint32_t)(j0 + u);
+                    }
+                    const unsigned bal = __ballot_sync(KODB_FULL_MASK, cold);
+                    if (bal) {
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(&s.cnt, __popc(bal));
+                        base = __shfl_sync(KODB_FULL_MASK, base, 0);
+                        if (cold) {
+                            const int pos = base + __popc(bal & ((1u << lane) - 1u));
+                            sc_img[pos] = conf;
+                            ky_img[pos] = k32;
+                            atomicAdd(&s.chist[bin], 1);
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+    __threadfence_block();
+    __syncthreads();
+    return n0 + s.cnt;
+}
+
 __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid_constant__ EvalParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NmsSmem& s = *reinterpret_cast<NmsSmem*>(smem_raw);
@@ -713,12 +1001,12 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
 
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int C = p.C;
-    const int n = p.img_count[b];
+    int n = p.img_count[b];  // listed candidates (floor mode: a subset of all candidates until the completion pass)
     const float* score = p.cand_score + (int64_t)b * p.cand_stride;
     const uint32_t* key = p.cand_key + (int64_t)b * p.cand_stride;
     const int max_det = p.cfg.max_det;
-    const bool rank_mode = n > p.cfg.max_nms;  // nms.py:61-63: candidates re-ordered by confidence, top max_nms kept
-    const int limit = rank_mode ? p.cfg.max_nms : n;
+    const bool floor_mode = p.floor_mode != 0;
+    const unsigned short* mask_img = p.mask + (int64_t)b * p.mask_stride;
     const double iou_thr = p.cfg.iou_thres;
     const float max_wh = p.cfg.max_wh;
     const int* ccount = p.chunk_count + (int64_t)b * p.chunks_per_image;
@@ -747,8 +1035,10 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
         s.chist[i] = p.hist[(int64_t)b * HB + i];
         p.hist[(int64_t)b * HB + i] = 0;
     }
-    // exclusive prefix of the per-chunk candidate counts (chunk order == key order of the tiles)
-    if (!rank_mode) {
+    // exclusive prefix of the per-chunk candidate counts (chunk order == key order of the tiles); in floor mode the
+    // chunk counts are the only place that knows the image's total number of candidates
+    int n_total = n;
+    if (floor_mode || n <= p.cfg.max_nms) {
         int carry = 0;
         for (int t0 = 0; t0 < p.chunks_per_image; t0 += NMS_THREADS) {
             const int t = t0 + tid;
@@ -758,8 +1048,19 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
             if (t < p.chunks_per_image) s.cprefix[t] = carry + ex;
             carry += tot;
         }
+        if (floor_mode) n_total = carry;
+    }
+    const bool rank_mode = n_total > p.cfg.max_nms;  // nms.py:61-63: candidates re-ordered by confidence, top max_nms kept
+    const int limit = rank_mode ? p.cfg.max_nms : n_total;
+    // floor mode: bins 0..avail-1 of the histogram are complete (every candidate of those bins is listed)
+    int avail = HB;
+    int floor_bin = HB - 1;
+    if (floor_mode) {
+        floor_bin = p.floor_word[b] - 1;
+        avail = floor_bin >= HB - 1 ? HB : floor_bin + 1;
     }
     __syncthreads();
+    if (floor_mode && tid == 0) p.floor_word[b] = 0;  // reusable without a memset
     KODB_TRACE(1);
 
     int nk = 0, processed = 0, k_target = K_TARGET0;
@@ -774,15 +1075,21 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
         if (!in_fine) {
             // ------------------------------------------------------------ cut from the coarse histogram
             if (tid == 0) s.sel_bin = -1;
-            const int v = (tid < HB && tid >= dnext) ? s.chist[tid] : 0;
+            const int v = (tid < avail && tid >= dnext) ? s.chist[tid] : 0;
             int total;
             const int ex = block_excl_scan(v, s.scan_tmp, &total);  // (barriers inside order sel_bin's reset)
             if (ex < k_target && ex + v >= k_target) { s.sel_bin = tid; s.sel_p = ex + v; s.sel_prev = ex; }
             if (tid < HB) { s.bstart[tid] = ex; s.bfill[tid] = 0; }
             __syncthreads();
-            if (total == 0) break;  // nothing left
+            if (total == 0) {
+                if (avail == HB) break;  // nothing left
+                // the listed candidates ran dry before max_det survivors: list the rest of the image from the masks
+                n = complete_list(p, s, b, n, floor_bin);
+                avail = HB;
+                continue;
+            }
             const int d = s.sel_bin, dfirst = dnext;
-            if (d < 0) { m = total; hi_batch = U64MAX; dnext = HB; }                     // fewer than k_target left: all
+            if (d < 0) { m = total; hi_batch = coarse_hi(avail - 1); dnext = avail; }     // fewer than k_target left: all
             else if (s.sel_p <= K_CAP) { m = s.sel_p; hi_batch = coarse_hi(d); dnext = d + 1; }
             else if (s.sel_prev > 0) { m = s.sel_prev; hi_batch = coarse_hi(d - 1); dnext = d; }
             else { in_fine = true; dnext = d; }  // bins before d are empty; d alone overflows the sort capacity
@@ -856,7 +1163,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int i = r0 + u * NMS_THREADS + tid;
-                    sv[u] = i < n4 ? __ldg(score4 + i) : make_float4(ninf, ninf, ninf, ninf);
+                    sv[u] = i < n4 ? __ldcg(score4 + i) : make_float4(ninf, ninf, ninf, ninf);
                 }
                 unsigned take = 0u;  // bit 4u + w
 #pragma unroll
@@ -880,7 +1187,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
                                 if ((take >> (4 * u + w)) & 1u) {
                                     const int d = coarse_bin(vv[w]);
                                     const int pos = s.bstart[d] + atomicAdd(&s.bfill[d], 1);
-                                    s.sort_ck[pos] = ((unsigned long long)desc_key(vv[w]) << 32) | __ldg(key + i + w);
+                                    s.sort_ck[pos] = ((unsigned long long)desc_key(vv[w]) << 32) | __ldcg(key + i + w);
                                 }
                         }
                     }
@@ -897,7 +1204,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
 #pragma unroll
                         for (int w = 0; w < 4; ++w)
                             if ((take >> (4 * u + w)) & 1u)
-                                s.sort_ck[pos++] = ((unsigned long long)desc_key(vv[w]) << 32) | __ldg(key + i + w);
+                                s.sort_ck[pos++] = ((unsigned long long)desc_key(vv[w]) << 32) | __ldcg(key + i + w);
                     }
                 }
             }
@@ -1259,7 +1566,31 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
     // nms.py:47: candidates are listed in (row, class) order, i.e. by ascending key.  index(key) = number of
     // candidates of the image with a smaller key = [chunks of earlier tiles] + [smaller keys inside the
     // chunks of its own tile].  One warp per survivor.
-    if (!rank_mode) {
+    if (!rank_mode && floor_mode) {
+        // from the class masks: candidates of earlier rows of the tile + earlier classes of the same row
+        for (int q = wid; q < nk; q += NMS_THREADS / 32) {
+            const uint32_t k32 = (uint32_t)s.kept_ck[q];
+            const int row = (int)(k32 / (uint32_t)C), j = (int)(k32 - (uint32_t)row * (uint32_t)C);
+            const int tl = tile_of_row(p, row);
+            int L, a, c0, ncell;
+            planar_tile(p.g, tl, L, a, c0, ncell);
+            const int row0 = p.g.row_base[L] + a * (p.g.lv[L].H * p.g.lv[L].W) + c0;
+            const int r = row - row0;
+            int cnt = 0;
+            for (int g = 0; g < p.ngroups; ++g) {
+                const unsigned short* mk = mask_img + (int64_t)g * p.rows + row0;
+                const int jl = j - g * CGROUP;  // classes of this group below j
+                const unsigned below = jl >= CGROUP ? 0xffffu : (jl <= 0 ? 0u : ((1u << jl) - 1u));
+                for (int i = lane; i <= r; i += 32) {
+                    const unsigned m16 = mk[i];
+                    cnt += __popc(i < r ? m16 : (m16 & below));
+                }
+            }
+            cnt = warp_sum_i(cnt);
+            if (lane == 0) s.kept_idx[q] = (long long)s.cprefix[tl * p.ngroups] + cnt;
+        }
+        __syncthreads();
+    } else if (!rank_mode) {
         for (int q = wid; q < nk; q += NMS_THREADS / 32) {
             const uint32_t k32 = (uint32_t)s.kept_ck[q];
             const int tl = tile_of_row(p, (int)(k32 / (uint32_t)C));
@@ -1299,7 +1630,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
     }
     if (tid == 0) {
         p.out.counts[b] = nk;
-        if (p.out.num_candidates) p.out.num_candidates[b] = n;
+        if (p.out.num_candidates) p.out.num_candidates[b] = n_total;
         p.img_count[b] = 0;  // workspace reusable without a memset
     }
     KODB_TRACE(7);
@@ -1376,22 +1707,27 @@ static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 static size_t cand_cap(int64_t rows, int C) { return ((size_t)rows * C + 3) & ~(size_t)3; }  // float4-aligned per image
 
+static size_t mask_cap(int64_t rows, int C) { return (((size_t)rows + 3) & ~(size_t)3) * ((C + CGROUP - 1) / CGROUP); }
+
 static int64_t ws_bytes(int batch, int64_t rows, int C, int chunks_per_image) {
     const size_t cap = cand_cap(rows, C);
-    return (int64_t)(align256((size_t)batch * 4) + align256((size_t)batch * HB * 4) +
-                     2 * align256((size_t)batch * chunks_per_image * 4) + 2 * align256((size_t)batch * cap * 4));
+    return (int64_t)(2 * align256((size_t)batch * 4) + align256((size_t)batch * HB * 4) +
+                     2 * align256((size_t)batch * chunks_per_image * 4) + 2 * align256((size_t)batch * cap * 4) +
+                     align256((size_t)batch * mask_cap(rows, C) * 2));
 }
 
 static int carve_ws(EvalParams& p, void* ws, int64_t ws_bytes_avail) {
     const size_t cap = cand_cap(p.rows, p.C);
     if (ws_bytes_avail < ws_bytes(p.B, p.rows, p.C, p.chunks_per_image)) return KODB_ERR_CAPACITY;
     char* w = reinterpret_cast<char*>(ws);
-    // the two zero-on-entry arrays sit at FIXED offsets so a cached workspace survives a geometry change
-    // as long as the batch size is the same; the host layer keys its cache on the full geometry anyway
+    // the zero-on-entry arrays come first, at offsets that depend on the batch size only (include/kodb.h: a
+    // workspace is reusable across calls with the same batch size)
     p.img_count = reinterpret_cast<int*>(w);
     w += align256((size_t)p.B * 4);
     p.hist = reinterpret_cast<int*>(w);
     w += align256((size_t)p.B * HB * 4);
+    p.floor_word = reinterpret_cast<int*>(w);
+    w += align256((size_t)p.B * 4);
     p.chunk_start = reinterpret_cast<int*>(w);
     w += align256((size_t)p.B * p.chunks_per_image * 4);
     p.chunk_count = reinterpret_cast<int*>(w);
@@ -1399,7 +1735,10 @@ static int carve_ws(EvalParams& p, void* ws, int64_t ws_bytes_avail) {
     p.cand_score = reinterpret_cast<float*>(w);
     w += align256((size_t)p.B * cap * 4);
     p.cand_key = reinterpret_cast<uint32_t*>(w);
+    w += align256((size_t)p.B * cap * 4);
     p.cand_stride = (int64_t)cap;
+    p.mask = reinterpret_cast<unsigned short*>(w);
+    p.mask_stride = (int64_t)mask_cap(p.rows, p.C);
     return KODB_OK;
 }
 
@@ -1428,6 +1767,7 @@ static int setup_match(EvalParams& p, const kodb_targets* gt, const kodb_match_o
 }
 
 static long long* g_trace = nullptr;
+static int g_hot_target = HOT_TARGET;
 
 static int launch_select(const EvalParams& p_in, cudaStream_t st) {
     EvalParams p = p_in;
@@ -1450,6 +1790,16 @@ static int launch_select(const EvalParams& p_in, cudaStream_t st) {
 
 // debug hook (not part of include/kodb.h): device buffer of B*128 int64 receiving per-image phase stamps
 extern "C" void kodb_debug_set_nms_trace(void* ptr) { kodb::g_trace = reinterpret_cast<long long*>(ptr); }
+// debug hook: the number of listed candidates per image the score floor aims at (small values force the
+// select kernel's completion pass; used by the parity tests).  <= 0 restores the default.
+// debug hook: number of completion passes (images whose listed candidates ran dry) since the last call; synchronises
+extern "C" int kodb_debug_take_completions(void) {
+    unsigned int v = 0u, z = 0u;
+    if (cudaMemcpyFromSymbol(&v, kodb::g_completions, sizeof(v)) != cudaSuccess) return -1;
+    cudaMemcpyToSymbol(kodb::g_completions, &z, sizeof(z));
+    return (int)v;
+}
+extern "C" void kodb_debug_set_hot_target(int n) { kodb::g_hot_target = n > 0 ? n : kodb::HOT_TARGET; }
 
 extern "C" int64_t kodb_eval_workspace_bytes(int32_t batch, int64_t rows_per_image, int32_t num_classes) {
     // upper bound of chunks per image: tiles <= ceil(rows/256) + one ragged tile per (level, anchor) plane
@@ -1481,6 +1831,10 @@ extern "C" int kodb_eval_tail(const kodb_head_level* heads_h, const kodb_level_c
     p.tiles_per_image = tiles;
     p.chunks_per_image = tiles * p.ngroups;
     p.trace = nullptr;
+    p.floor_mode = vec == 4;
+    p.sample_stride = (tiles + CW_WARPS - 1) / CW_WARPS;  // at most one sample tile per warp of the sample CTA
+    p.ns = (tiles + p.sample_stride - 1) / p.sample_stride;
+    p.hot_target = g_hot_target;
     if (p.chunks_per_image > CHUNK_CAP) return KODB_ERR_UNSUPPORTED;
     if ((rc = carve_ws(p, workspace, workspace_bytes)) != KODB_OK) return rc;
     if ((rc = setup_match(p, gt_h, match_h)) != KODB_OK) return rc;
@@ -1488,10 +1842,11 @@ extern "C" int kodb_eval_tail(const kodb_head_level* heads_h, const kodb_level_c
     const int stages = cfg_h->stage_mask ? cfg_h->stage_mask : 3;
     if (stages & 1) {
         if (vec == 4) {
-            const dim3 grid((tiles + CW_WARPS - 1) / CW_WARPS, batch);
+            const dim3 grid((unsigned)(batch + ((int64_t)(tiles - p.ns) * batch + CW_WARPS - 1) / CW_WARPS));
             const int nq = p.C < CGROUP ? p.C : CGROUP;
             rc = nq <= 4 ? launch_cand_warp<4>(p, grid, st) : nq <= 8 ? launch_cand_warp<8>(p, grid, st)
-                 : nq <= 12 ? launch_cand_warp<12>(p, grid, st) : launch_cand_warp<16>(p, grid, st);
+                 : nq <= 10 ? launch_cand_warp<10>(p, grid, st) : nq <= 12 ? launch_cand_warp<12>(p, grid, st)
+                                                                            : launch_cand_warp<16>(p, grid, st);
             if (rc != KODB_OK) return rc;
         } else {
             cand_kernel<true, 1><<<dim3(tiles, batch), CAND_THREADS, 0, st>>>(p);
@@ -1522,6 +1877,10 @@ extern "C" int kodb_nms(const float* detections, int32_t batch, int64_t rows, co
     p.tiles_per_image = (int)((rows + CAND_THREADS - 1) / CAND_THREADS);
     p.chunks_per_image = p.tiles_per_image * p.ngroups;
     p.trace = nullptr;
+    p.floor_mode = 0;
+    p.ns = 0;
+    p.sample_stride = 1;
+    p.hot_target = 0;
     if (p.chunks_per_image > CHUNK_CAP) return KODB_ERR_UNSUPPORTED;
     if ((rc = carve_ws(p, workspace, workspace_bytes)) != KODB_OK) return rc;
     if ((rc = setup_match(p, gt_h, match_h)) != KODB_OK) return rc;

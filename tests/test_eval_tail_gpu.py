@@ -127,6 +127,37 @@ def test_fused_eval_tail_equals_decode_then_nms(B, S, C, shift, oracle_lib):
     assert torch.equal(fused.dets, two_step.dets) and torch.equal(fused.keep_idx, two_step.keep_idx)
 
 
+@pytest.mark.parametrize("target", [1, 64, 600, 100000])
+@pytest.mark.parametrize("B,S,C,shift", [(3, 640, 10, 0.0), (2, 320, 80, 1.0)])
+def test_fused_floor_completion(target, B, S, C, shift, oracle_lib):
+    """The score floor of the candidate kernel is a performance device only: whatever floor the sampling picks
+    (forced very high here, so the select kernel must complete the list from the class masks, and very low, so
+    everything is listed), keeps, rows and keep indices equal kodb_nms(kodb_decode()) bit for bit."""
+    from object_detection_cib_b200 import _lib as L
+    heads = syn.make_head(B, S, C, seed=11 * S + C, obj_shift=shift)
+    targets = syn.make_targets(B, S, C, seed=4)
+    syn.inject_ground_truth(heads, targets, S)
+    dh = _to_dev(heads)
+    shape, info = FeatureShape(S, S), default_anchor_info()
+    want = N.nms_padded(N.get_detections(shape, dh, info), 0.001, 0.6)
+    lib = L.lib()
+    lib.kodb_debug_set_hot_target(int(target))
+    lib.kodb_debug_take_completions()
+    try:
+        got = N.eval_tail(shape, dh, info, 0.001, 0.6)
+        torch.cuda.synchronize()
+    finally:
+        lib.kodb_debug_set_hot_target(0)
+    completions = lib.kodb_debug_take_completions()
+    if target <= 64:
+        assert completions > 0, "a floor this high must force the completion pass"
+    if target >= 100000:
+        assert completions == 0
+    assert torch.equal(got.counts, want.counts)
+    assert torch.equal(got.dets, want.dets) and torch.equal(got.keep_idx, want.keep_idx)
+    assert torch.equal(got.num_candidates, want.num_candidates)
+
+
 def _match_oracle(dets_list, targets, C):
     o = om.CocoMapOracle(C)
     ms = []

@@ -30,7 +30,7 @@ torch.cuda.synchronize()
 lib.kodb_debug_set_nms_trace(None)
 t = trace.cpu().numpy().reshape(B, 128)
 names = {0: "start", 1: "tileprefix", 2: "select", 3: "collect", 4: "sort", 5: "decode", 6: "nms_compact", 7: "output", 8: "match", 10: "nms_bucket", 11: "nms_scatter", 12: "nms_tiles", 13: "nms_resolve"}
-print("ncand", res.num_candidates[:8].tolist(), "kept", res.counts[:8].tolist())
+print("ncand", res.num_candidates[:8].tolist(), "kept", res.counts[:8].tolist(), "completions", lib.kodb_debug_take_completions())
 tot = {}
 for b in range(B):
     n = int(t[b, 0])
