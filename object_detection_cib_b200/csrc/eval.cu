@@ -34,7 +34,7 @@ constexpr int CGROUP = 16;       // classes per pass of the candidate kernel
 constexpr int HB = 512;          // coarse score-histogram bins per image (32 per octave below 1.0)
 constexpr int NB = 4096;         // fine histogram bins per refinement level
 constexpr int K_CAP = 1024;      // sort capacity = one element per thread (batch size upper bound)
-constexpr int K_TARGET0 = 448;   // preferred size of the first batch; doubled for later batches
+constexpr int K_TARGET0 = 352;   // preferred size of the first batch (max_det 300 + slack); doubled for later batches
 constexpr int NMS_THREADS = 1024;
 constexpr int NMS_STEP = 128;     // candidates resolved per NMS step (4 per warp)
 constexpr int MAX_DET_CAP = 1024;
@@ -159,6 +159,20 @@ __device__ __forceinline__ float4 fetch_box(const EvalParams& p, int b, int row)
     const int64_t bo = (int64_t)b * hd.box_sb + (int64_t)a * hd.box_sa + cell;
     return decode_box(hd.box[bo], hd.box[bo + hd.box_sp], hd.box[bo + 2 * hd.box_sp], hd.box[bo + 3 * hd.box_sp], (float)gx,
                       (float)gy, (float)lv.stride, lv.anchor_px[a][0], lv.anchor_px[a][1]);
+}
+
+// L2 prefetch of the four box logits (or the decoded row) a later fetch_box(p, b, row) will read
+__device__ __forceinline__ void prefetch_box(const EvalParams& p, int b, int row) {
+    if (!p.planar) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.det + ((int64_t)b * p.rows + row) * (5 + p.C)));
+        return;
+    }
+    int L, a, cell;
+    planar_row(p.g, row, L, a, cell);
+    const kodb_head_level& hd = p.g.head[L];
+    const float* q = hd.box + (int64_t)b * hd.box_sb + (int64_t)a * hd.box_sa + cell;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + k * hd.box_sp));
 }
 
 // =========================================================================================================
@@ -349,6 +363,7 @@ __device__ __forceinline__ unsigned long long expand_nibbles(unsigned a16) {  //
 }
 
 constexpr int HOT_TARGET = 2048;
+constexpr int FLOOR_POLLS = 0;      // optional bounded wait for the floor at the second chance (measured: no gain on B200)
 
 // smallest positive score of coarse bin d (d < HB - 1)
 __device__ __forceinline__ float coarse_lower_edge(int d) { return __uint_as_float(((0x3F800000u >> 18) - (uint32_t)d) << 18); }
@@ -576,8 +591,18 @@ __global__ void __launch_bounds__(CW_WARPS * 32, 3) cand_floor_kernel(const __gr
             *reinterpret_cast<uint2*>(p.mask + (int64_t)b * p.mask_stride + (int64_t)grp * p.rows + row0 + cell0) =
                 make_uint2(cm[0] | (cm[1] << 16), cm[2] | (cm[3] << 16));
         if (full && !sample) {
-            // second chance: the floor may have been published while this tile was streaming
-            const int w = *(const volatile int*)(p.floor_word + b);
+            // second chance: the floor may have been published while this tile was streaming; a first-wave tile
+            // gives the sample CTA a few microseconds (bounded: nothing here depends on another CTA's progress)
+            int w = 0;
+            if (lane == 0) {
+                const volatile int* fw = p.floor_word + b;
+                w = *fw;
+                for (int tries = 0; w == 0 && tries < FLOOR_POLLS; ++tries) {
+                    __nanosleep(100);
+                    w = *fw;
+                }
+            }
+            w = __shfl_sync(KODB_FULL_MASK, w, 0);
             if (w > 0 && w - 1 < HB - 1) {
                 floor_bin = w - 1;
                 full = false;
@@ -754,6 +779,7 @@ struct NmsSmem {
 };
 constexpr int RANK_CAP = 192;  // bins up to this population are ordered by counting; a heavier bin falls back to the bitonic sort
 static_assert(sizeof(NmsSmem) <= 180 * 1024, "NmsSmem budget");
+static_assert(GT_CAP <= NMS_THREADS, "the select kernel stages one ground-truth box per thread");
 static_assert(NB >= 32 * KODB_MAX_CLASSES, "per-(warp, class) counts alias the fine histogram");
 
 __device__ __forceinline__ bool suppresses(float ax1, float ay1, float ax2, float ay2, float aarea, float bx1, float by1,
@@ -1001,20 +1027,41 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
 
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int C = p.C;
+    const bool floor_mode = p.floor_mode != 0;
+    const int* ccount = p.chunk_count + (int64_t)b * p.chunks_per_image;
+    const int* cstart = p.chunk_start + (int64_t)b * p.chunks_per_image;
+    // every independent global load of the prologue is issued before the first use (one L2 round trip, not five)
     int n = p.img_count[b];  // listed candidates (floor mode: a subset of all candidates until the completion pass)
+    const int hist_v = tid < HB ? p.hist[(int64_t)b * HB + tid] : 0;
+    const int cc0 = tid < p.chunks_per_image ? ccount[tid] : 0;
+    const int floor_w = floor_mode ? p.floor_word[b] : 0;
+    int g0 = 0, gt_n = 0;
+    if (p.do_match) {
+        g0 = p.gt_offsets[b];
+        gt_n = p.gt_offsets[b + 1] - g0;
+    }
     const float* score = p.cand_score + (int64_t)b * p.cand_stride;
     const uint32_t* key = p.cand_key + (int64_t)b * p.cand_stride;
     const int max_det = p.cfg.max_det;
-    const bool floor_mode = p.floor_mode != 0;
     const unsigned short* mask_img = p.mask + (int64_t)b * p.mask_stride;
     const double iou_thr = p.cfg.iou_thres;
     const float max_wh = p.cfg.max_wh;
-    const int* ccount = p.chunk_count + (int64_t)b * p.chunks_per_image;
-    const int* cstart = p.chunk_start + (int64_t)b * p.chunks_per_image;
 
     int trace_n = 0;
     KODB_TRACE(0);
+    if (p.trace && tid == 0) {
+        long long gt0;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt0));
+        p.trace[(int64_t)b * 128 + 1] = gt0;
+    }
     if (tid == 0) { s.nk = 0; }
+    // ground truth of the image: loaded now (one box per thread), stored to shared memory after the scans below
+    long long gt_lab = -1;
+    double gt_l = 0.0, gt_t = 0.0, gt_r = 0.0, gt_b = 0.0;
+    if (tid < gt_n) {
+        gt_lab = p.gt_labels[g0 + tid];
+        load_gt_xyxy(p.gt_boxes, p.gt_dtype, g0 + tid, gt_l, gt_t, gt_r, gt_b);
+    }
     // Class-bucketed NMS is exact iff boxes of different classes cannot intersect after the class offset: every
     // raw coordinate inside a window no wider than max_wh, class offsets j*max_wh exact in fp32 (rounding of
     // x + offset is monotone, so disjoint stays disjoint), and a threshold >= 0 (zero overlap never suppresses).
@@ -1023,17 +1070,10 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
     const float thr_rd = __double2float_rd(iou_thr);
     const float thr_hi = thr_rd * 1.000001f, thr_lo = thr_rd * 0.999999f;  // guard band of the approximate ratio test
     cls_static = __syncthreads_and(tid >= C || (double)((float)tid * max_wh) == (double)tid * (double)max_wh) && cls_static;
-    // ground truth of the image -> shared memory now; the loads overlap the whole selection / NMS phase
-    int gt_n = 0;
-    if (p.do_match) {
-        const int g0 = p.gt_offsets[b];
-        gt_n = p.gt_offsets[b + 1] - g0;
-        stage_gt(gs, C, p.gt_boxes, p.gt_labels, g0, gt_n, p.gt_dtype, p.m);
-    }
     // coarse score histogram of the image (accumulated by the candidate kernel); reset for the next launch
-    for (int i = tid; i < HB; i += NMS_THREADS) {
-        s.chist[i] = p.hist[(int64_t)b * HB + i];
-        p.hist[(int64_t)b * HB + i] = 0;
+    if (tid < HB) {
+        s.chist[tid] = hist_v;
+        p.hist[(int64_t)b * HB + tid] = 0;
     }
     // exclusive prefix of the per-chunk candidate counts (chunk order == key order of the tiles); in floor mode the
     // chunk counts are the only place that knows the image's total number of candidates
@@ -1042,7 +1082,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
         int carry = 0;
         for (int t0 = 0; t0 < p.chunks_per_image; t0 += NMS_THREADS) {
             const int t = t0 + tid;
-            const int v = t < p.chunks_per_image ? ccount[t] : 0;
+            const int v = t0 == 0 ? cc0 : (t < p.chunks_per_image ? ccount[t] : 0);
             int tot;
             const int ex = block_excl_scan(v, s.scan_tmp, &tot);
             if (t < p.chunks_per_image) s.cprefix[t] = carry + ex;
@@ -1056,11 +1096,19 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
     int avail = HB;
     int floor_bin = HB - 1;
     if (floor_mode) {
-        floor_bin = p.floor_word[b] - 1;
+        floor_bin = floor_w - 1;
         avail = floor_bin >= HB - 1 ? HB : floor_bin + 1;
+        if (tid == 0) p.floor_word[b] = 0;  // reusable without a memset
+    }
+    if (p.do_match) {  // (GT_CAP == NMS_THREADS: one ground-truth box per thread)
+        for (int i = tid; i < KODB_NUM_IOU_THRS * gt_n; i += NMS_THREADS) gs.taken[i / gt_n][i % gt_n] = 0;
+        if (tid < gt_n) {
+            if (gt_lab >= 0 && gt_lab < C) atomicAdd(reinterpret_cast<unsigned long long*>(p.m.gt_count) + gt_lab, 1ull);
+            gs.gx[tid] = gt_l; gs.gy[tid] = gt_t; gs.gw[tid] = gt_r - gt_l; gs.gh[tid] = gt_b - gt_t;  // [l, t, r-l, b-t]
+            gs.glabel[tid] = (int)gt_lab;
+        }
     }
     __syncthreads();
-    if (floor_mode && tid == 0) p.floor_word[b] = 0;  // reusable without a memset
     KODB_TRACE(1);
 
     int nk = 0, processed = 0, k_target = K_TARGET0;
@@ -1217,6 +1265,8 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
         __syncthreads();
         KODB_TRACE(3);
         if (!binned) m = s.cnt;  // == the histogram count
+        // the box logits of the batch have not been touched yet (DRAM): start fetching them while the batch is sorted
+        if (tid < m) prefetch_box(p, b, (int)((uint32_t)s.sort_ck[tid] / (uint32_t)C));
         if (binned) {
             // bins are already in place (descending score = ascending bin); order every segment by counting the
             // smaller composite keys inside it (keys are unique)
@@ -1644,6 +1694,11 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
         match_image(ms, gs, nk, C, gt_n, p.m, b, max_det);
     }
     KODB_TRACE(8);
+    if (p.trace && tid == 0) {
+        long long gt1;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt1));
+        p.trace[(int64_t)b * 128 + 127] = gt1;
+    }
 }
 
 // standalone matching on NMS output (B, max_det, 6)

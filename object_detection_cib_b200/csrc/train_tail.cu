@@ -55,9 +55,19 @@ struct TrainParams {
     int dense_grid;
     double* dense_partials;   // [TD_MAX_GRID][3]   softplus sums per level
     double* sparse_partials;  // [B*3][3]           (loc, obj correction, cls) per (image, level)
-    unsigned int* counter;    // zero on entry, zero on exit
+    unsigned int* counter;    // sparse CTAs that published their loss partials; zero on entry, zero on exit
+    unsigned int* counter2;   // sparse CTAs that are completely done; zero on entry, zero on exit
     int* nl_pub;              // [3] N_l published by the b == 0 CTAs for the finaliser
     unsigned int* dense_done; // completion counter of the dense CTAs; zero on entry / exit
+    // chunk queue of the dense stream (all levels contiguous): chunk ids are handed out by an atomic counter, so a
+    // CTA that is served slower by the memory system simply takes fewer chunks
+    int use_queue;
+    unsigned int* queue;                       // zero on entry / exit
+    int ch_obj, ch_zero;                       // float4 per objectness chunk / per zero-fill chunk
+    int n_obj_chunks[KODB_NUM_LEVELS];         // chunks of the level's objectness plane
+    int n_box_chunks[KODB_NUM_LEVELS], n_cls_chunks[KODB_NUM_LEVELS];
+    int n_chunks;                              // all chunks
+    int n_partials;                            // fp64 softplus partials the finaliser sums (queue: one per obj chunk)
     long long* trace;         // debug: per-CTA phase stamps (globaltimer ns), NULL in production
 };
 
@@ -116,6 +126,82 @@ __device__ __forceinline__ int64_t strided_off(int64_t i, int HW, int P, int A, 
     return b * sb + a * sa + (int64_t)pl * sp + cell;
 }
 
+// Dense stream over a chunk queue.  Chunk order: per level [objectness chunks | box zero-fill | cls zero-fill].  An
+// objectness chunk reads its logits (all loads of the thread issued first), writes dobj = s*sigmoid(x) and stores
+// the chunk's fp64 softplus sum at a fixed place (dense_partials[chunk]) -- the finaliser adds the partials in chunk
+// order, so the loss does not depend on which CTA took which chunk.  The next ticket is requested before the
+// current chunk is processed (the atomic's round trip is hidden).
+__device__ __forceinline__ void dense_queue(const TrainParams& p, const float up[3], double* red_tmp, int* ticket_sm) {
+    constexpr int OBJ_PER_THREAD = 4, ZERO_PER_THREAD = 8;  // float4 per thread and chunk (chunk sizes are multiples)
+    const int tid = threadIdx.x;
+    // the first chunk of a CTA is its block index (no atomic); tickets from the counter start behind those
+    unsigned next = blockIdx.x;
+    for (;;) {
+        __syncthreads();  // the previous round's readers of ticket_sm are done
+        if (tid == 0) {
+            ticket_sm[0] = (int)next;
+            if ((int)next < p.n_chunks) next = (unsigned)p.dense_grid + atomicAdd(p.queue, 1u);  // prefetch the next ticket
+        }
+        __syncthreads();
+        int c = ticket_sm[0];
+        if (c >= p.n_chunks) break;
+        int L = 0, kind = 0;  // kind 0: obj, 1: box, 2: cls
+        for (;;) {
+            if (c < p.n_obj_chunks[L]) { kind = 0; break; }
+            c -= p.n_obj_chunks[L];
+            if (c < p.n_box_chunks[L]) { kind = 1; break; }
+            c -= p.n_box_chunks[L];
+            if (c < p.n_cls_chunks[L]) { kind = 2; break; }
+            c -= p.n_cls_chunks[L];
+            ++L;
+        }
+        const kodb_level_cfg& lv = p.lv[L];
+        const int64_t n_obj = (int64_t)p.B * lv.num_anchors * lv.H * lv.W;
+        if (kind == 0) {
+            const int64_t n4 = n_obj >> 2, i0 = (int64_t)c * p.ch_obj;
+            const int64_t i1 = i0 + p.ch_obj < n4 ? i0 + p.ch_obj : n4;
+            const float s_obj = (float)((double)up[1] * p.lam_obj * (double)lv.obj_ratio / (double)n_obj);
+            const float4* src = reinterpret_cast<const float4*>(p.head[L].obj);
+            float4* dst = reinterpret_cast<float4*>(p.grad[L].obj);
+            float a0 = 0.0f;
+            for (int64_t base = i0; base < i1; base += OBJ_PER_THREAD * TD_THREADS) {
+                float4 x[OBJ_PER_THREAD];
+#pragma unroll
+                for (int u = 0; u < OBJ_PER_THREAD; ++u) {
+                    const int64_t i = base + u * TD_THREADS + tid;
+                    x[u] = i < i1 ? __ldcs(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < OBJ_PER_THREAD; ++u) {
+                    const int64_t i = base + u * TD_THREADS + tid;
+                    if (i < i1) {
+                        float s0, s1, s2, s3;
+                        const float v0 = softplus_sigmoid_fast(x[u].x, &s0), v1 = softplus_sigmoid_fast(x[u].y, &s1);
+                        const float v2 = softplus_sigmoid_fast(x[u].z, &s2), v3 = softplus_sigmoid_fast(x[u].w, &s3);
+                        a0 += (v0 + v1) + (v2 + v3);
+                        if (p.has_grads) __stcs(dst + i, make_float4(s_obj * s0, s_obj * s1, s_obj * s2, s_obj * s3));
+                    }
+                }
+            }
+            int pidx = c;  // index of this objectness chunk among all objectness chunks
+            for (int l = 0; l < L; ++l) pidx += p.n_obj_chunks[l];
+            const double sum = block_sum_d((double)a0, red_tmp);
+            if (tid == 0) p.dense_partials[pidx] = sum;
+        } else {
+            const int64_t n4 = kind == 1 ? n_obj : (n_obj >> 2) * p.C;  // float4 of the box / cls planes
+            float4* dst = reinterpret_cast<float4*>(kind == 1 ? p.grad[L].box : p.grad[L].cls);
+            const int64_t i0 = (int64_t)c * p.ch_zero;
+            const int64_t i1 = i0 + p.ch_zero < n4 ? i0 + p.ch_zero : n4;
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int64_t base = i0 + tid; base < i1; base += ZERO_PER_THREAD * TD_THREADS) {
+#pragma unroll
+                for (int u = 0; u < ZERO_PER_THREAD; ++u)
+                    if (base + u * TD_THREADS < i1) __stcs(dst + base + u * TD_THREADS, z);
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ void dense_cta(const TrainParams& p, const float up[3], double* red_tmp, int* cnt_tmp) {
     TT_TRACE(0);
     // N_l = number of assigned rows per level over the whole batch: the first B dense CTAs count one image
@@ -138,6 +224,16 @@ __device__ __forceinline__ void dense_cta(const TrainParams& p, const float up[3
         __syncthreads();
         if (threadIdx.x < KODB_NUM_LEVELS && cnt_tmp[threadIdx.x]) atomicAdd(&p.nl_pub[threadIdx.x], cnt_tmp[threadIdx.x]);
         __syncthreads();
+    }
+    if (p.use_queue) {
+        dense_queue(p, up, red_tmp, cnt_tmp);
+        __syncthreads();  // every thread's stores are issued
+        if (threadIdx.x == 0) {
+            __threadfence();  // release: stores of this CTA visible device-wide before the counter moves
+            atomicAdd(p.dense_done, 1u);
+        }
+        TT_TRACE(1);
+        return;
     }
     const int64_t gtid = (int64_t)blockIdx.x * TD_THREADS + threadIdx.x;
     const int64_t gsize = (int64_t)p.dense_grid * TD_THREADS;
@@ -420,9 +516,24 @@ __device__ __forceinline__ void sparse_cta(const TrainParams& p, const float up[
     }
     TT_TRACE(2);
 
+    // ---- loss partials -> workspace now (they do not depend on the dense stream); the CTA that publishes last
+    // becomes the finaliser and reduces everything in a fixed order while the others are still patching ---------
+    const double pl_ = block_sum_d(acc_loc, red_tmp);
+    const double po_ = block_sum_d(acc_obj, red_tmp);
+    const double pc_ = block_sum_d(acc_cls, red_tmp);
+    const unsigned nblocks = gridDim.x - p.dense_grid;
+    if (tid == 0) {
+        double* dst = p.sparse_partials + ((size_t)b * KODB_NUM_LEVELS + L) * 3;
+        dst[0] = pl_; dst[1] = po_; dst[2] = pc_;
+        __threadfence();
+        const unsigned prev = atomicAdd(p.counter, 1u);
+        s_last = (prev == nblocks - 1);
+    }
+    __syncthreads();
     // ---- wait for the dense stream: everything above overlapped it; the patches below must land on top ----
     if (tid == 0) {
-        while (atomicAdd(p.dense_done, 0u) < (unsigned)p.dense_grid) __nanosleep(100);
+        // plain (L2) loads: polling with an atomic would queue up behind the dense CTAs' increments of the same word
+        while (*(const volatile unsigned int*)p.dense_done < (unsigned)p.dense_grid) __nanosleep(200);
         __threadfence();  // acquire (also orders the N_l counters the dense CTAs accumulated)
     }
     __syncthreads();
@@ -478,22 +589,9 @@ __device__ __forceinline__ void sparse_cta(const TrainParams& p, const float up[
     }
     TT_TRACE(4);
 
-    // ---- partials -> workspace; the last CTA finalises in a fixed order -----------------------------------
-    const double pl_ = block_sum_d(acc_loc, red_tmp);
-    const double po_ = block_sum_d(acc_obj, red_tmp);
-    const double pc_ = block_sum_d(acc_cls, red_tmp);
-    const unsigned nblocks = gridDim.x - p.dense_grid;
-    if (tid == 0) {
-        double* dst = p.sparse_partials + ((size_t)b * KODB_NUM_LEVELS + L) * 3;
-        dst[0] = pl_; dst[1] = po_; dst[2] = pc_;
-        __threadfence();
-        const unsigned prev = atomicAdd(p.counter, 1u);
-        s_last = (prev == nblocks - 1);
-    }
-    __syncthreads();
     TT_TRACE(5);
-    if (!s_last) return;
-    __threadfence();
+    if (s_last) {
+    // (the partials were released with a fence before the counter moved and are read through L2 below)
     // all loads first (independent, L2), then ONE block reduction of the nine sums in a fixed order
     double v[9];
 #pragma unroll
@@ -506,9 +604,17 @@ __device__ __forceinline__ void sparse_cta(const TrainParams& p, const float up[
         for (int q = 0; q < KODB_NUM_LEVELS; ++q)
             if (q == l) { v[q] += a0; v[3 + q] += a1; v[6 + q] += a2; }
     }
-    for (int i = tid; i < p.dense_grid; i += TS_THREADS) {
-        const double* src = p.dense_partials + (size_t)i * 3;
-        v[3] += __ldcg(src); v[4] += __ldcg(src + 1); v[5] += __ldcg(src + 2);
+    if (p.use_queue) {
+        const int e0 = p.n_obj_chunks[0], e1 = e0 + p.n_obj_chunks[1];
+        for (int i = tid; i < p.n_partials; i += TS_THREADS) {
+            const double a = __ldcg(p.dense_partials + i);
+            if (i < e0) v[3] += a; else if (i < e1) v[4] += a; else v[5] += a;
+        }
+    } else {
+        for (int i = tid; i < p.dense_grid; i += TS_THREADS) {
+            const double* src = p.dense_partials + (size_t)i * 3;
+            v[3] += __ldcg(src); v[4] += __ldcg(src + 1); v[5] += __ldcg(src + 2);
+        }
     }
     double* red9 = reinterpret_cast<double*>(smem_raw);  // rows are dead; >= 8 warps * 9 doubles available
 #pragma unroll
@@ -539,11 +645,22 @@ __device__ __forceinline__ void sparse_cta(const TrainParams& p, const float up[
         p.losses[0] = (float)(p.lam_loc * loc);
         p.losses[1] = (float)(p.lam_obj * obj);
         p.losses[2] = (float)(p.lam_cls * cls);
-        *p.counter = 0u;
-        *p.dense_done = 0u;
-        p.nl_pub[0] = 0; p.nl_pub[1] = 0; p.nl_pub[2] = 0;
+    }
     }
     TT_TRACE(6);
+    // ---- the CTA that finishes last (patches written, losses out) resets the control words for the next launch
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const unsigned prev2 = atomicAdd(p.counter2, 1u);
+        if (prev2 == nblocks - 1) {
+            *p.counter = 0u;
+            *p.counter2 = 0u;
+            *p.dense_done = 0u;
+            *p.queue = 0u;
+            p.nl_pub[0] = 0; p.nl_pub[1] = 0; p.nl_pub[2] = 0;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(TS_THREADS, 4) train_tail_kernel(const __grid_constant__ TrainParams p) {
@@ -627,6 +744,31 @@ extern "C" int kodb_train_tail(const kodb_head_level* heads_h, const kodb_level_
         }
         p.contiguous[l] = ok ? 1 : 0;
     }
+    // chunk queue of the dense stream (needs every level flat and float4-divisible)
+    p.use_queue = 1;
+    for (int l = 0; l < KODB_NUM_LEVELS; ++l) {
+        const int64_t n_obj = (int64_t)p.B * p.lv[l].num_anchors * p.lv[l].H * p.lv[l].W;
+        if (!p.contiguous[l] || (n_obj & 3)) p.use_queue = 0;
+    }
+    p.n_chunks = p.n_partials = 0;
+    p.ch_obj = 4 * TD_THREADS;
+    p.ch_zero = 16 * TD_THREADS;  // 64 KB: few enough tickets for one atomic counter, fine enough to balance
+    if (p.use_queue) {
+        int64_t tot4 = 0;
+        for (int l = 0; l < KODB_NUM_LEVELS; ++l) tot4 += ((int64_t)p.B * p.lv[l].num_anchors * p.lv[l].H * p.lv[l].W) >> 2;
+        // objectness chunks are the fp64 partials of the finaliser: keep their number inside the workspace
+        const int64_t max_partials = (int64_t)TD_MAX_GRID * 3 - KODB_NUM_LEVELS;
+        while ((tot4 + p.ch_obj - 1) / p.ch_obj > max_partials) p.ch_obj *= 2;
+        for (int l = 0; l < KODB_NUM_LEVELS; ++l) {
+            const int64_t n_obj = (int64_t)p.B * p.lv[l].num_anchors * p.lv[l].H * p.lv[l].W;
+            const int64_t n4 = n_obj >> 2;
+            p.n_obj_chunks[l] = (int)((n4 + p.ch_obj - 1) / p.ch_obj);
+            p.n_box_chunks[l] = p.has_grads ? (int)((n_obj + p.ch_zero - 1) / p.ch_zero) : 0;
+            p.n_cls_chunks[l] = p.has_grads ? (int)((n4 * p.C + p.ch_zero - 1) / p.ch_zero) : 0;
+            p.n_partials += p.n_obj_chunks[l];
+            p.n_chunks += p.n_obj_chunks[l] + p.n_box_chunks[l] + p.n_cls_chunks[l];
+        }
+    }
     p.row_cap = 5 * amax * (t->max_per_image > 0 ? t->max_per_image : 1);
     size_t smem = (size_t)p.row_cap * (6 * sizeof(int) + sizeof(float4));
     if (smem > 160 * 1024) return KODB_ERR_CAPACITY;  // > ~270 boxes in ONE image (reference data has <= ~72)
@@ -639,6 +781,8 @@ extern "C" int kodb_train_tail(const kodb_head_level* heads_h, const kodb_level_
     p.counter = reinterpret_cast<unsigned int*>(w);
     p.nl_pub = reinterpret_cast<int*>(w + 64);
     p.dense_done = reinterpret_cast<unsigned int*>(w + 128);
+    p.queue = reinterpret_cast<unsigned int*>(w + 192);
+    p.counter2 = reinterpret_cast<unsigned int*>(w + 200);
     w += 256;
     p.dense_partials = reinterpret_cast<double*>(w);
     w += tt_align((size_t)TD_MAX_GRID * 3 * sizeof(double));
@@ -669,6 +813,13 @@ extern "C" int kodb_train_tail(const kodb_head_level* heads_h, const kodb_level_
         if (per_sm < 1 || per_sm > 8) per_sm = 3;
     }
     int grid_dense = c_sms[dev] * per_sm;
+    if (p.use_queue) {
+        // every sparse CTA should be resident from the start (its row phase overlaps the dense stream, and it must
+        // not queue up behind dense CTAs): leave it a slot out of the 4 CTAs/SM the kernel's launch bounds allow
+        const int slots = c_sms[dev] * 4, n_sparse = p.B * KODB_NUM_LEVELS;
+        if (grid_dense > slots - n_sparse) grid_dense = slots - n_sparse;
+        if (grid_dense < c_sms[dev]) grid_dense = c_sms[dev];
+    }
     if (grid_dense > TD_MAX_GRID) grid_dense = TD_MAX_GRID;
     p.dense_grid = grid_dense;
     p.trace = g_tt_trace;

@@ -28,9 +28,20 @@ for it in range(3):
     res, rec = N.eval_tail(FeatureShape(S, S), net, default_anchor_info(), 0.001, 0.6, targets=targets, gt_count=gt_count)
 torch.cuda.synchronize()
 lib.kodb_debug_set_nms_trace(None)
+# wall time of the two kernels of one call (CUDA events), same inputs, for comparison with the in-kernel stamps
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+times = []
+for it in range(10):
+    ev[0].record()
+    N.eval_tail(FeatureShape(S, S), net, default_anchor_info(), 0.001, 0.6, targets=targets, gt_count=gt_count)
+    ev[1].record()
+    torch.cuda.synchronize()
+    times.append(ev[0].elapsed_time(ev[1]) * 1e3)
+print("eval_tail call (python launch + both kernels) us: min", min(times), "median", sorted(times)[5])
 t = trace.cpu().numpy().reshape(B, 128)
 names = {0: "start", 1: "tileprefix", 2: "select", 3: "collect", 4: "sort", 5: "decode", 6: "nms_compact", 7: "output", 8: "match", 10: "nms_bucket", 11: "nms_scatter", 12: "nms_tiles", 13: "nms_resolve"}
 print("ncand", res.num_candidates[:8].tolist(), "kept", res.counts[:8].tolist(), "completions", lib.kodb_debug_take_completions())
+print("select kernel: first CTA start -> last CTA end (globaltimer) us", (t[:, 127].max() - t[:, 1].min()) / 1e3, "per-CTA span mean/max us", ((t[:, 127] - t[:, 1]) / 1e3).mean(), ((t[:, 127] - t[:, 1]) / 1e3).max(), "start spread us", (t[:, 1].max() - t[:, 1].min()) / 1e3)
 tot = {}
 for b in range(B):
     n = int(t[b, 0])
