@@ -127,6 +127,33 @@ def test_fused_eval_tail_equals_decode_then_nms(B, S, C, shift, oracle_lib):
     assert torch.equal(fused.dets, two_step.dets) and torch.equal(fused.keep_idx, two_step.keep_idx)
 
 
+@pytest.mark.parametrize("B,S,C,check", [(128, 640, 10, (0, 63, 127)), (2, 1280, 80, (1,)), (3, 416, 10, (0, 1, 2))])
+def test_fused_full_size_configs(B, S, C, check, oracle_lib):
+    """BASELINE configs at full size: eval batch 128/GPU at 640 (cfg 3), the 80-class 1280x1280 head (cfg 5, more than
+    max_nms candidates per image: the top-30000 cut) and the reference's default 416 input (13x13 grid: the
+    non-float4 path).  The fused path must equal kodb_nms(kodb_decode()) on every image, and the oracle NMS applied
+    to our decode on the spot-checked ones."""
+    heads = syn.make_head(B, S, C, seed=S + C + B)
+    targets = syn.make_targets(B, S, C, seed=6)
+    syn.inject_ground_truth(heads, targets, S)
+    dh = _to_dev(heads)
+    shape, info = FeatureShape(S, S), default_anchor_info()
+    det = N.get_detections(shape, dh, info)
+    two_step = N.nms_padded(det, 0.001, 0.6)
+    fused = N.eval_tail(shape, dh, info, 0.001, 0.6)
+    assert torch.equal(fused.counts, two_step.counts)
+    assert torch.equal(fused.dets, two_step.dets) and torch.equal(fused.keep_idx, two_step.keep_idx)
+    assert torch.equal(fused.num_candidates, two_step.num_candidates)
+    sub = det[list(check)].cpu().numpy()
+    ref = on.non_max_suppression(sub, 0.001, 0.6)
+    counts = fused.counts.cpu().numpy()
+    for r, b in zip(ref, check):
+        n = counts[b]
+        assert n == r.dets.shape[0]
+        assert np.array_equal(fused.keep_idx[b, :n].cpu().numpy(), r.keep)
+        assert np.array_equal(fused.dets[b, :n].cpu().numpy().view(np.uint32), r.dets.view(np.uint32))
+
+
 @pytest.mark.parametrize("target", [1, 64, 600, 100000])
 @pytest.mark.parametrize("B,S,C,shift", [(3, 640, 10, 0.0), (2, 320, 80, 1.0)])
 def test_fused_floor_completion(target, B, S, C, shift, oracle_lib):

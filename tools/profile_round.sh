@@ -1,0 +1,11 @@
+#!/bin/bash
+# Round profile pass (run on the GPU box through gpurun): plain run first (must exit 0), then the ncu launch list of
+# the same command, then one `--set full` capture of each of the three kernels of a step.  Outputs -> gpurun_out/.
+set -u
+TAG=${1:-r1_final}
+CMD="python bench.py --steps 6 --warmup 3 --no-e2e --no-cpu-baseline --no-graph"
+$CMD > gpurun_out/${TAG}_plain.json 2> gpurun_out/${TAG}_plain.err || { echo "plain run failed"; tail -5 gpurun_out/${TAG}_plain.err; exit 1; }
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_launches.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'train_tail_kernel|cand_floor_kernel|select_nms_kernel' -s 12 -c 3 \
+    -o gpurun_out/${TAG}_full $CMD > gpurun_out/${TAG}_ncu_full.log 2>&1
+ls -la gpurun_out/${TAG}_*

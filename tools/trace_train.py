@@ -17,23 +17,27 @@ from object_detection_cib_b200.types import DetectionHeadResult, FeatureShape, d
 
 B, S, C = 64, 640, 10
 dev = torch.device("cuda:0")
-heads = syn.make_head(B, S, C, seed=2023, device=dev)
+NSETS = 3  # rotate inputs and gradient buffers like bench.py does (3 x ~200 MB > L2)
 targets = syn.make_targets(B, S, C, seed=2023)
-net = [DetectionHeadResult(*lv) for lv in heads]
 mod = Yolov5Loss(Yolov5LabelAssigner(default_anchor_info()), Yolov5LossParams.get_default(), IoUCalculator(IoUType.ciou),
                  syn.readme_class_weights())
-plan = mod.plan(FeatureShape(S, S), net, targets)
-grads = [H.alloc_planar_like(t) for t in plan.heads.tensors]
+plans, gradsets = [], []
+for k in range(NSETS):
+    heads = syn.make_head(B, S, C, seed=2023 + k, device=dev)
+    net = [DetectionHeadResult(*lv) for lv in heads]
+    plan = mod.plan(FeatureShape(S, S), net, targets)
+    plans.append(plan)
+    gradsets.append([H.alloc_planar_like(t) for t in plan.heads.tensors])
 losses = torch.zeros(3, device=dev)
 nass = torch.zeros(3, dtype=torch.int32, device=dev)
 lib = L.lib()
 lib.kodb_debug_set_train_trace.argtypes = [ctypes.c_void_p]
 NG = 148 * 8 + B * 3
 trace = torch.zeros(NG * 8, dtype=torch.long, device=dev)
-for it in range(4):
-    if it == 3:
+for it in range(7):
+    if it == 6:
         lib.kodb_debug_set_train_trace(trace.data_ptr())
-    launch_train_tail(plan, (float(B),) * 3, None, 0, grads, losses, nass)
+    launch_train_tail(plans[it % NSETS], (float(B),) * 3, None, 0, gradsets[it % NSETS], losses, nass)
 torch.cuda.synchronize()
 lib.kodb_debug_set_train_trace(None)
 t = trace.cpu().numpy().reshape(NG, 8).astype(np.float64)
