@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--no-fork", action="store_true", help="serialise the train and eval tails inside the graph")
     ap.add_argument("--fork", choices=("late", "early"), default="late",
                     help="late: candidates -> (select/NMS || train tail); early: eval tail || train tail from the start")
+    ap.add_argument("--pipeline", type=int, default=1, choices=(0, 1),
+                    help="1: replay the graph of input set s on its own stream (consecutive steps overlap); 0: one stream")
     ap.add_argument("--train-delay-cycles", type=int, default=0,
                     help="--fork late: spin this many SM cycles on the train stream before the train tail is launched")
     ap.add_argument("--cpu-sample", type=int, default=8, help="images in the cpu_baseline sample")
@@ -176,6 +178,8 @@ def run_ours(a):
         syn.inject_ground_truth(heads, targets, S, fraction=0.3, seed=seed)
         net = [DetectionHeadResult(*lv) for lv in heads]
         plan = loss_mod.plan(shape, net, targets)
+        # one train workspace per input set: steps of different sets may be in flight at the same time (--pipeline)
+        plan = plan._replace(workspace=H.workspace(f"train{s}", dev, plan.workspace.numel()))
         grads = [H.alloc_planar_like(t) for t in plan.heads.tensors]
         losses = torch.zeros(3, dtype=torch.float32, device=dev)
         nass = torch.zeros(3, dtype=torch.int32, device=dev)
@@ -265,11 +269,32 @@ def run_ours(a):
             graphs = None
             torch.cuda.synchronize(dev)
 
+    # Steps are independent (each input set has its own buffers, outputs and workspaces): with --pipeline the graph
+    # of set s is always replayed on replay stream s, so up to NSETS consecutive steps are in flight and the
+    # latency-bound select/NMS kernel of one step overlaps the streaming kernels of the next.
+    rstreams = [torch.cuda.Stream(device=dev) for _ in range(NSETS)] if (a.pipeline and graphs is not None) else None
+
     def step(i):
         if graphs is not None:
-            graphs[i % NSETS].replay()
+            if rstreams is not None:
+                with torch.cuda.stream(rstreams[i % NSETS]):
+                    graphs[i % NSETS].replay()
+            else:
+                graphs[i % NSETS].replay()
         else:
             step_eager(i)
+
+    def fork_replay_streams():
+        if rstreams is not None:
+            cur = torch.cuda.current_stream(dev)
+            for r in rstreams:
+                r.wait_stream(cur)
+
+    def join_replay_streams():
+        if rstreams is not None:
+            cur = torch.cuda.current_stream(dev)
+            for r in rstreams:
+                cur.wait_stream(r)
 
     def barrier():
         if world > 1:
@@ -282,14 +307,18 @@ def run_ours(a):
         time.sleep(0.15)
 
     # ---- warm-up + the timed region: EXACTLY K steps ------------------------------------------------------
+    fork_replay_streams()
     for i in range(max(a.warmup, 3)):
         step(i)
+    join_replay_streams()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_load0 = time.time()
     e0.record()
+    fork_replay_streams()  # the replay streams start behind e0 ...
     for i in range(a.steps):
         step(i)
+    join_replay_streams()  # ... and e1 is recorded behind the last kernel of every one of them
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -339,11 +368,26 @@ def run_ours(a):
         d2h = sum(t.numel() * t.element_size() for t in host_out.values())
         ev_e2e = DeviceCocoMapEvaluator(Cn, device=dev)
 
-        def e2e_step():
-            net = []
-            for lv in host_heads:
-                d = [t.to(dev, non_blocking=True).permute(0, 1, 3, 4, 2).requires_grad_(True) for t in lv]
-                net.append(DetectionHeadResult(*d))
+        # Double-buffered: the H2D copy of step i+1 (copy stream) overlaps the kernels and the D2H of step i; the host
+        # waits for the results of step i-1 before it issues step i+1's copies, and for the last one before the clock
+        # stops -- every step's inputs cross PCIe and every step's results reach the host inside the timed region.
+        copy_stream = torch.cuda.Stream(device=dev)
+        dev_in = [[[torch.empty_like(t, device=dev) for t in lv] for lv in host_heads] for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
+
+        def e2e_upload(k):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done[k % 2])  # the buffers' previous step has been consumed
+                for lv_d, lv_h in zip(dev_in[k % 2], host_heads):
+                    for td, th in zip(lv_d, lv_h):
+                        td.copy_(th, non_blocking=True)
+                ready[k % 2].record(copy_stream)
+
+        def e2e_compute(k):
+            cur = torch.cuda.current_stream(dev)
+            cur.wait_event(ready[k % 2])
+            net = [DetectionHeadResult(*[t.permute(0, 1, 3, 4, 2).detach().requires_grad_(True) for t in lv]) for lv in dev_in[k % 2]]
             r = loss_mod(shape, net, st["targets"])  # packs + uploads the targets
             total = B * (r.localization + r.classification + r.objectness)  # exp.py:124-130
             total.backward()
@@ -352,15 +396,23 @@ def run_ours(a):
             host_out["dets"].copy_(res.dets, non_blocking=True)
             host_out["counts"].copy_(res.counts, non_blocking=True)
             host_out["tp"].copy_(rec.tp, non_blocking=True)
-            torch.cuda.synchronize(dev)  # the step's results are on the host
+            done[k % 2].record(cur)
+
+        def e2e_run(n):
+            e2e_upload(0)
+            for k in range(n):
+                if k + 1 < n:
+                    e2e_upload(k + 1)
+                e2e_compute(k)
+                if k >= 1:
+                    done[(k - 1) % 2].synchronize()  # step k-1's results are on the host
+            torch.cuda.synchronize(dev)
 
         n_e2e = max(3, min(a.steps, 30))
-        for _ in range(3):
-            e2e_step()
+        e2e_run(3)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            e2e_step()
+        e2e_run(n_e2e)
         barrier()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -368,7 +420,7 @@ def run_ours(a):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * B * n_e2e / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "steps": n_e2e,
-               "api": "Yolov5Loss.forward+backward, nms.eval_tail (pinned host head maps -> device -> pinned host results)"}
+               "api": "Yolov5Loss.forward+backward, nms.eval_tail (pinned host head maps -> device -> pinned host results; H2D of step i+1 overlaps step i)"}
 
     # ---- epoch-end exchange (the only collective of the path): gather records + global AP ---------------
     evaluator.reset()  # the timed loops accumulated GT counts for thousands of steps; start a clean "epoch"
@@ -420,7 +472,9 @@ def run_ours(a):
                        "l2": f"inputs rotate over {NSETS} sets ({NSETS}x{(b_eval * B) / 1e6:.0f} MB head + grads) > 126 MB L2",
                        "launch": (("cuda-graph replay: candidate kernel, then select/NMS kernel || train tail on two captured streams"
                                    if a.fork == "late" else "cuda-graph replay, train tail || eval tail on two captured streams")
-                                  if not a.no_fork else "cuda-graph replay, serial") if graphs is not None else "eager async launches"},
+                                  if not a.no_fork else "cuda-graph replay, serial") + (
+                                      f"; consecutive steps pipelined over {NSETS} replay streams (one per input set)" if a.pipeline else "")
+                       if graphs is not None else "eager async launches"},
             "gpu_launches": LAUNCHES_PER_STEP * a.steps,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
