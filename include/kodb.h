@@ -89,7 +89,8 @@ typedef struct kodb_targets {
     int32_t boxes_dtype;        /* KODB_BOXES_F32 / KODB_BOXES_F64 */
     int32_t num_targets;        /* T */
     int32_t batch;              /* B */
-    int32_t max_per_image;      /* max_b (img_offsets[b+1]-img_offsets[b]), known on the host */
+    int32_t max_per_image;      /* max_b (img_offsets[b+1]-img_offsets[b]), known on the host; the matching stage
+                                   takes at most 512 boxes per image (KODB_ERR_CAPACITY beyond) */
 } kodb_targets;
 
 /* Yolov5LossParams (loss.py:25-43) + IoUCalculator(iou_type, eps) (iou.py:249-268). */
@@ -154,7 +155,7 @@ typedef struct kodb_nms_cfg {
     float conf_thres;   /* compared in fp32 (torch casts the python scalar to the tensor dtype) */
     double iou_thres;   /* torchvision CPU kernel compares the fp32 ratio with this double */
     float max_wh;       /* 4096 */
-    int32_t max_det;    /* 300 */
+    int32_t max_det;    /* 300; at most 512 */
     int32_t max_nms;    /* 30000 */
     int32_t num_classes;
     uint32_t class_mask[KODB_MAX_CLASSES / 32]; /* `classes` filter; all ones = None */

@@ -32,13 +32,14 @@ namespace kodb {
 constexpr int CAND_THREADS = 256;
 constexpr int CGROUP = 16;       // classes per pass of the candidate kernel
 constexpr int HB = 512;          // coarse score-histogram bins per image (32 per octave below 1.0)
-constexpr int NB = 4096;         // fine histogram bins per refinement level
-constexpr int K_CAP = 1024;      // sort capacity = one element per thread (batch size upper bound)
+constexpr int NMS_THREADS = 512;  // two select CTAs fit on an SM (registers, shared memory), or one next to other kernels
+constexpr int LOG_NB = 11;
+constexpr int NB = 1 << LOG_NB;  // fine histogram bins per refinement level (4 per thread)
+constexpr int K_CAP = NMS_THREADS;  // sort capacity = one element per thread (batch size upper bound)
 constexpr int K_TARGET0 = 352;   // preferred size of the first batch (max_det 300 + slack); doubled for later batches
-constexpr int NMS_THREADS = 1024;
-constexpr int NMS_STEP = 128;     // candidates resolved per NMS step (4 per warp)
-constexpr int MAX_DET_CAP = 1024;
-constexpr int GT_CAP = 1024;     // max ground-truth boxes of ONE image in the matching stage
+constexpr int NMS_STEP = NMS_THREADS / 8;  // candidates resolved per step of the generic NMS path (4 per warp)
+constexpr int MAX_DET_CAP = NMS_THREADS;  // max_det <= 512 (the reference uses 300)
+constexpr int GT_CAP = NMS_THREADS;  // max ground-truth boxes of ONE image in the matching stage
 constexpr int CHUNK_CAP = 4096;  // max candidate chunks (tiles x class groups) per image
 constexpr unsigned long long U64MAX = 0xffffffffffffffffull;
 
@@ -65,6 +66,7 @@ struct EvalParams {
     int* hist;         // [B][HB]   zero on entry / exit
     int* chunk_start;  // [B][chunks_per_image]
     int* chunk_count;  // [B][chunks_per_image]
+    int* chunk_prefix; // [B][chunks_per_image]  written and read by the select kernel
     int tiles_per_image, chunks_per_image;
     // floor mode (planar float4 path): only candidates at or above a per-image score floor are listed; every
     // candidate is recorded as a bit in `mask` (keep indices, the rare completion pass)
@@ -758,7 +760,6 @@ constexpr int CLS_WORDS = CLS_CAP / 32;  // suppression-mask words per candidate
 struct NmsSmem {
     int hist[NB];  // fine histogram of the radix refinement; aliased by the per-(warp, class) counts of the NMS phase
     int chist[HB];
-    int cprefix[CHUNK_CAP];
     unsigned long long sort_ck[K_CAP];
     float bx1[K_CAP], by1[K_CAP], bx2[K_CAP], by2[K_CAP], barea[K_CAP];      // batch, score order
     float4 cbox[K_CAP];  // batch, class-major order (x1, y1, x2, y2 with the class offset)
@@ -778,9 +779,9 @@ struct NmsSmem {
     int cnt, nk, cls_over;
 };
 constexpr int RANK_CAP = 192;  // bins up to this population are ordered by counting; a heavier bin falls back to the bitonic sort
-static_assert(sizeof(NmsSmem) <= 180 * 1024, "NmsSmem budget");
+static_assert(NB == 4 * NMS_THREADS, "the radix refinement reads four fine bins per thread");
 static_assert(GT_CAP <= NMS_THREADS, "the select kernel stages one ground-truth box per thread");
-static_assert(NB >= 32 * KODB_MAX_CLASSES, "per-(warp, class) counts alias the fine histogram");
+static_assert(NB >= (NMS_THREADS / 32) * KODB_MAX_CLASSES, "per-(warp, class) counts alias the fine histogram");
 
 __device__ __forceinline__ bool suppresses(float ax1, float ay1, float ax2, float ay2, float aarea, float bx1, float by1,
                                            float bx2, float by2, float barea, double thr) {
@@ -813,6 +814,7 @@ struct GtSmem {
 constexpr size_t kNmsRegion =
     ((sizeof(NmsSmem) > sizeof(MatchSmem) ? sizeof(NmsSmem) : sizeof(MatchSmem)) + 15) & ~(size_t)15;
 constexpr size_t kMatchRegion = (sizeof(MatchSmem) + 15) & ~(size_t)15;
+static_assert(kNmsRegion + sizeof(GtSmem) <= 113 * 1024, "two select CTAs per SM");
 
 __device__ __forceinline__ void load_gt_xyxy(const void* boxes, int dtype, int g, double& l, double& t, double& r, double& b) {
     if (dtype == KODB_BOXES_F64) {
@@ -932,11 +934,11 @@ __device__ void match_image(MatchSmem& ms, GtSmem& gs, int nk, int C, int ng, co
 // Floor mode, rare: the listed candidates ran dry before max_det survivors.  Lists every candidate of the image
 // that the candidate kernel left out (pairs of tiles not listed in full whose score lies in a bin below the floor), straight
 // from the class masks and the head logits, appends them to the image's list and completes the histogram.
-// Eight warps, one tile at a time each; scratch on top of the batch arrays (free between batches).  Block-wide.
+// Four warps, one tile at a time each; scratch on top of the batch arrays (free between batches).  Block-wide.
 __device__ unsigned int g_completions = 0u;  // debug statistic: completion passes since the last query
 
 __device__ int complete_list(const EvalParams& p, NmsSmem& s, int b, int n0, int floor_bin) {
-    constexpr int CL_WARPS = 8;
+    constexpr int CL_WARPS = 4;
     if (threadIdx.x == 0) atomicAdd(&g_completions, 1u);
     static_assert(sizeof(s.pm) >= CL_WARPS * WT_CELLS * CGROUP * sizeof(unsigned short), "id lists fit in pm");
     static_assert(sizeof(s.bx1) >= CL_WARPS * WT_CELLS * sizeof(float), "objectness fits in bx1");
@@ -1019,7 +1021,7 @@ __device__ int complete_list(const EvalParams& p, NmsSmem& s, int b, int n0, int
     return n0 + s.cnt;
 }
 
-__global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid_constant__ EvalParams p) {
+__global__ void __launch_bounds__(NMS_THREADS, 2) select_nms_kernel(const __grid_constant__ EvalParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NmsSmem& s = *reinterpret_cast<NmsSmem*>(smem_raw);
     MatchSmem& ms = *reinterpret_cast<MatchSmem*>(smem_raw);  // aliases NmsSmem: used after NMS is finished
@@ -1030,6 +1032,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
     const bool floor_mode = p.floor_mode != 0;
     const int* ccount = p.chunk_count + (int64_t)b * p.chunks_per_image;
     const int* cstart = p.chunk_start + (int64_t)b * p.chunks_per_image;
+    int* cprefix = p.chunk_prefix + (int64_t)b * p.chunks_per_image;  // exclusive prefix of the chunk counts (written below)
     // every independent global load of the prologue is issued before the first use (one L2 round trip, not five)
     int n = p.img_count[b];  // listed candidates (floor mode: a subset of all candidates until the completion pass)
     const int hist_v = tid < HB ? p.hist[(int64_t)b * HB + tid] : 0;
@@ -1085,7 +1088,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
             const int v = t0 == 0 ? cc0 : (t < p.chunks_per_image ? ccount[t] : 0);
             int tot;
             const int ex = block_excl_scan(v, s.scan_tmp, &tot);
-            if (t < p.chunks_per_image) s.cprefix[t] = carry + ex;
+            if (t < p.chunks_per_image) cprefix[t] = carry + ex;
             carry += tot;
         }
         if (floor_mode) n_total = carry;
@@ -1155,7 +1158,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
             {
                 const unsigned long long span = ghi - glo - 1ull;
                 const int nbits = span ? 64 - __clzll((long long)span) : 0;
-                shift = nbits > 12 ? nbits - 12 : 0;
+                shift = nbits > LOG_NB ? nbits - LOG_NB : 0;
             }
             for (;;) {
                 for (int i = tid; i < NB; i += NMS_THREADS) s.hist[i] = 0;
@@ -1188,7 +1191,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
                 glo = blo; ghi = bhi; rlo = blo;
                 const unsigned long long span = ghi - glo - 1ull;
                 const int nbits = span ? 64 - __clzll((long long)span) : 0;
-                shift = nbits > 12 ? nbits - 12 : 0;
+                shift = nbits > LOG_NB ? nbits - LOG_NB : 0;
                 __syncthreads();
             }
             if (hi_batch == fine_hi) { in_fine = false; dnext += 1; }  // the coarse bin is exhausted by this batch
@@ -1357,7 +1360,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
                     bx.w >= win_lo && bx.w <= win_hi);
         }
         if (cls_static) {
-            for (int i = tid; i < 32 * C; i += NMS_THREADS) s.hist[i] = 0;  // per-(warp, class) counts
+            for (int i = tid; i < (NMS_THREADS / 32) * C; i += NMS_THREADS) s.hist[i] = 0;  // per-(warp, class) counts
         }
         if (__syncthreads_or(bad)) cls_static = false;  // sticky: a kept out-of-window box may reach across classes later
         bool cls_path = cls_static;
@@ -1377,9 +1380,9 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
             if (my_c >= 0 && rank == 0) s.hist[wid * C + my_c] = __popc(peers);
             __syncthreads();
             for (int c = wid; c < C; c += NMS_THREADS / 32) {  // exclusive prefix over the warps, per class (lane = warp)
-                const int v = s.hist[lane * C + c];
+                const int v = lane < NMS_THREADS / 32 ? s.hist[lane * C + c] : 0;
                 const int ex = warp_excl_scan_i(v, lane);
-                s.hist[lane * C + c] = ex;
+                if (lane < NMS_THREADS / 32) s.hist[lane * C + c] = ex;
                 if (lane == 31) s.ccount[c] = ex + v;
             }
             __syncthreads();
@@ -1637,7 +1640,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
                 }
             }
             cnt = warp_sum_i(cnt);
-            if (lane == 0) s.kept_idx[q] = (long long)s.cprefix[tl * p.ngroups] + cnt;
+            if (lane == 0) s.kept_idx[q] = (long long)__ldcg(cprefix + tl * p.ngroups) + cnt;
         }
         __syncthreads();
     } else if (!rank_mode) {
@@ -1652,7 +1655,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) select_nms_kernel(const __grid
                 for (int i = lane; i < nc; i += 32) cnt += (kk[i] < k32);
             }
             cnt = warp_sum_i(cnt);
-            if (lane == 0) s.kept_idx[q] = (long long)s.cprefix[tl * p.ngroups] + cnt;
+            if (lane == 0) s.kept_idx[q] = (long long)__ldcg(cprefix + tl * p.ngroups) + cnt;
         }
         __syncthreads();
     }
@@ -1767,7 +1770,7 @@ static size_t mask_cap(int64_t rows, int C) { return (((size_t)rows + 3) & ~(siz
 static int64_t ws_bytes(int batch, int64_t rows, int C, int chunks_per_image) {
     const size_t cap = cand_cap(rows, C);
     return (int64_t)(2 * align256((size_t)batch * 4) + align256((size_t)batch * HB * 4) +
-                     2 * align256((size_t)batch * chunks_per_image * 4) + 2 * align256((size_t)batch * cap * 4) +
+                     3 * align256((size_t)batch * chunks_per_image * 4) + 2 * align256((size_t)batch * cap * 4) +
                      align256((size_t)batch * mask_cap(rows, C) * 2));
 }
 
@@ -1786,6 +1789,8 @@ static int carve_ws(EvalParams& p, void* ws, int64_t ws_bytes_avail) {
     p.chunk_start = reinterpret_cast<int*>(w);
     w += align256((size_t)p.B * p.chunks_per_image * 4);
     p.chunk_count = reinterpret_cast<int*>(w);
+    w += align256((size_t)p.B * p.chunks_per_image * 4);
+    p.chunk_prefix = reinterpret_cast<int*>(w);
     w += align256((size_t)p.B * p.chunks_per_image * 4);
     p.cand_score = reinterpret_cast<float*>(w);
     w += align256((size_t)p.B * cap * 4);
