@@ -805,12 +805,13 @@ extern "C" int kodb_train_tail(const kodb_head_level* heads_h, const kodb_level_
         c_smem[dev] = smem;
     }
     // dense CTAs first (lowest block ids are scheduled first and never wait), then one sparse CTA per
-    // (image, level).  Three dense CTAs per SM leave room for the sparse ones to run concurrently.
+    // (image, level).  Two dense CTAs per SM (chunk queue: 296 CTAs already reach the fill rate of the HBM) leave room
+    // for the sparse ones and for the other kernels of a pipelined step to run concurrently.
     static int per_sm = 0;
     if (per_sm == 0) {
         const char* e = getenv("KODB_TRAIN_DENSE_PER_SM");  // tuning knob; default chosen on B200
-        per_sm = e ? atoi(e) : 3;
-        if (per_sm < 1 || per_sm > 8) per_sm = 3;
+        per_sm = e ? atoi(e) : 2;
+        if (per_sm < 1 || per_sm > 8) per_sm = 2;
     }
     int grid_dense = c_sms[dev] * per_sm;
     if (p.use_queue) {
