@@ -185,6 +185,45 @@ def test_fused_floor_completion(target, B, S, C, shift, oracle_lib):
     assert torch.equal(got.num_candidates, want.num_candidates)
 
 
+_FUZZ = [
+    # B, S, C, conf, iou, obj_shift, hot_target
+    (1, 320, 1, 0.001, 0.6, 2.0, 0), (2, 320, 3, 0.01, 0.3, 3.0, 0), (3, 512, 17, 0.001, 0.6, 1.0, 0),
+    (2, 640, 10, 0.25, 0.45, 4.0, 0), (5, 320, 10, 0.001, 0.6, 0.0, 50), (2, 512, 33, 0.001, 0.5, 2.0, 200),
+    (1, 640, 80, 0.001, 0.6, 2.0, 0), (4, 352, 10, 0.001, 0.6, 5.0, 0), (2, 640, 16, 0.05, 0.7, 3.0, 30),
+    (3, 384, 2, 0.001, 0.6, 6.0, 0), (2, 448, 10, 0.001, 0.0, 2.0, 0), (1, 640, 10, 0.001, 0.6, 8.0, 0),
+]
+
+
+@pytest.mark.parametrize("B,S,C,conf,iou,shift,target", _FUZZ)
+def test_fused_fuzz(B, S, C, conf, iou, shift, target, oracle_lib):
+    """Geometry / class-count / threshold sweep (odd grids, 1..80 classes, dense and sparse candidate regimes, IoU
+    threshold 0, forced completion passes): the fused path equals kodb_nms(kodb_decode()) everywhere and the oracle
+    NMS applied to our decode on image 0."""
+    from object_detection_cib_b200 import _lib as L
+    heads = syn.make_head(B, S, C, seed=S * 7 + C * 3 + B, obj_shift=shift)
+    targets = syn.make_targets(B, S, C, seed=S + C)
+    syn.inject_ground_truth(heads, targets, S)
+    dh = _to_dev(heads)
+    shape, info = FeatureShape(S, S), default_anchor_info()
+    det = N.get_detections(shape, dh, info)
+    two_step = N.nms_padded(det, conf, iou)
+    lib = L.lib()
+    lib.kodb_debug_set_hot_target(int(target))
+    try:
+        fused = N.eval_tail(shape, dh, info, conf, iou)
+        torch.cuda.synchronize()
+    finally:
+        lib.kodb_debug_set_hot_target(0)
+    assert torch.equal(fused.counts, two_step.counts)
+    assert torch.equal(fused.dets, two_step.dets) and torch.equal(fused.keep_idx, two_step.keep_idx)
+    assert torch.equal(fused.num_candidates, two_step.num_candidates)
+    ref = on.non_max_suppression(det[:1].cpu().numpy(), conf, iou)[0]
+    n = int(fused.counts[0])
+    assert n == ref.dets.shape[0]
+    assert np.array_equal(fused.keep_idx[0, :n].cpu().numpy(), ref.keep)
+    assert np.array_equal(fused.dets[0, :n].cpu().numpy().view(np.uint32), ref.dets.view(np.uint32))
+
+
 def _match_oracle(dets_list, targets, C):
     o = om.CocoMapOracle(C)
     ms = []
