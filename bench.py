@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "yolov5s_tail_images_per_s"
 UNIT = "images/s"
-NSETS = 3  # rotating input sets: 3 x (96.8 MB head + 96.8 MB grads) >> 126 MB L2
+NSETS = int(os.environ.get("KODB_BENCH_NSETS", "3"))  # rotating input sets: 3 x (96.8 MB head + 96.8 MB grads) >> 126 MB L2
 
 
 def parse_args():

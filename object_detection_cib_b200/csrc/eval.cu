@@ -72,6 +72,7 @@ struct EvalParams {
     // candidate is recorded as a bit in `mask` (keep indices, the rare completion pass)
     int floor_mode;
     int ns, sample_stride;     // sample tiles per image: tiles 0, S, 2S, ... (one per warp of the image's sample CTA)
+    unsigned magic_b, magic_s1; // ceil(2^32 / B), ceil(2^32 / (S - 1)) when exact over the grid's index range, else 0
     int hot_target;            // estimated number of listed candidates per image the floor aims at
     int* floor_word;           // [B]  (floor bin + 1), 0 = not published yet; zero on entry / exit
     unsigned short* mask;      // [B][ngroups][rows]  bit u: class 16*group + u of the row is a candidate
@@ -428,9 +429,11 @@ __global__ void __launch_bounds__(CW_WARPS * 32, 3) cand_floor_kernel(const __gr
     } else {
         const int g2 = ((int)blockIdx.x - B) * CW_WARPS + wid;
         if (g2 >= nr * B) return;
-        const int ri = g2 / B;
+        // (divisions by multiply-high with host-checked magic numbers; 0 = not exact for this geometry, divide)
+        const int ri = p.magic_b ? (int)__umulhi((unsigned)g2, p.magic_b) : g2 / B;
         b = g2 - ri * B;
-        t = ri + ri / (S - 1) + 1;  // ri-th tile index that is not a multiple of S (S >= 2 whenever nr > 0)
+        const int rq = p.magic_s1 ? (int)__umulhi((unsigned)ri, p.magic_s1) : ri / (S - 1);
+        t = ri + rq + 1;  // ri-th tile index that is not a multiple of S (S >= 2 whenever nr > 0)
     }
     if (!active) {  // idle warp of a sample CTA: only the block barrier in front of the floor computation
         __syncthreads();
@@ -452,14 +455,15 @@ __global__ void __launch_bounds__(CW_WARPS * 32, 3) cand_floor_kernel(const __gr
     // Asynchronous 16-byte copies global -> the warp's shared stash (LDGSTS): all of the tile's bytes are in flight
     // at once without holding registers, so three CTAs fit on an SM.  The obj logits land in sm.o and are replaced
     // by their sigmoid below.
+    const unsigned sq0 = (unsigned)__cvta_generic_to_shared(&sm.q[0][cell0]);  // class u of the stash: + u * 512 bytes
     if (in_range) cp_async16(&sm.o[cell0], obj_base + cell0);
     else *reinterpret_cast<float4*>(&sm.o[cell0]) = zero4;
     {
-        const int jn = min(C, CGROUP);
+        const int nld = in_range ? min(C, CGROUP) : 0;
         const float* cp = cls_base + cell0;
 #pragma unroll
         for (int u = 0; u < NQ; ++u) {
-            if (in_range && u < jn) cp_async16(&sm.q[u][cell0], cp);
+            if (u < nld) cp_async16_s(sq0 + u * (WT_CELLS * 4), cp);
             else *reinterpret_cast<float4*>(&sm.q[u][cell0]) = zero4;
             cp += cls_step;
         }
@@ -522,9 +526,10 @@ __global__ void __launch_bounds__(CW_WARPS * 32, 3) cand_floor_kernel(const __gr
         if (grp > 0) {
             __syncwarp();  // the previous group's readers of the stash are done
             const float* cp = cls_base + (int64_t)j0 * cls_step + cell0;
+            const int nld = in_range ? jn : 0;
 #pragma unroll
             for (int u = 0; u < NQ; ++u) {
-                if (in_range && u < jn) cp_async16(&sm.q[u][cell0], cp);
+                if (u < nld) cp_async16_s(sq0 + u * (WT_CELLS * 4), cp);
                 else *reinterpret_cast<float4*>(&sm.q[u][cell0]) = zero4;
                 cp += cls_step;
             }
@@ -1829,6 +1834,15 @@ static int setup_match(EvalParams& p, const kodb_targets* gt, const kodb_match_o
 static long long* g_trace = nullptr;
 static int g_hot_target = HOT_TARGET;
 
+// m = ceil(2^32 / d) with umulhi(n, m) == n / d for every n <= n_max, or 0 if that does not hold
+static unsigned magic_div(unsigned d, uint64_t n_max) {
+    if (d < 2) return 0u;
+    const uint64_t m = ((1ull << 32) + d - 1) / d;
+    const uint64_t e = m * d - (1ull << 32);  // 0 <= e < d;  exact while n * e < 2^32
+    if (m >= (1ull << 32) || n_max * e >= (1ull << 32)) return 0u;
+    return (unsigned)m;
+}
+
 static int launch_select(const EvalParams& p_in, cudaStream_t st) {
     EvalParams p = p_in;
     p.trace = g_trace;
@@ -1894,6 +1908,8 @@ extern "C" int kodb_eval_tail(const kodb_head_level* heads_h, const kodb_level_c
     p.floor_mode = vec == 4;
     p.sample_stride = (tiles + CW_WARPS - 1) / CW_WARPS;  // at most one sample tile per warp of the sample CTA
     p.ns = (tiles + p.sample_stride - 1) / p.sample_stride;
+    p.magic_b = magic_div((unsigned)batch, (uint64_t)tiles * batch + CW_WARPS);
+    p.magic_s1 = p.sample_stride > 1 ? magic_div((unsigned)(p.sample_stride - 1), (uint64_t)tiles) : 0u;
     p.hot_target = g_hot_target;
     if (p.chunks_per_image > CHUNK_CAP) return KODB_ERR_UNSUPPORTED;
     if ((rc = carve_ws(p, workspace, workspace_bytes)) != KODB_OK) return rc;
@@ -1940,6 +1956,7 @@ extern "C" int kodb_nms(const float* detections, int32_t batch, int64_t rows, co
     p.floor_mode = 0;
     p.ns = 0;
     p.sample_stride = 1;
+    p.magic_b = p.magic_s1 = 0u;
     p.hot_target = 0;
     if (p.chunks_per_image > CHUNK_CAP) return KODB_ERR_UNSUPPORTED;
     if ((rc = carve_ws(p, workspace, workspace_bytes)) != KODB_OK) return rc;
