@@ -451,6 +451,19 @@ def run_ours(a):
     report = evaluator.get_report()
     epoch_end_ms = (time.perf_counter() - t0) * 1e3
 
+    # diagnostic: share of the candidate kernel's warp tiles that listed ALL their candidates in the last eval call (tiles
+    # that ran before the image's score floor was published, plus the sample tiles); eval.cu carve_ws layout
+    full_tiles = None
+    try:
+        tiles = sum(lv.num_anchors * ((lv.H * lv.W + 127) // 128) for lv in sets[0]["levels"])
+        groups = (Cn + 15) // 16
+        al = lambda v: (v + 255) // 256 * 256
+        off = al(B * 4) + al(B * 512 * 4) + al(B * 4)
+        flags = sets[0]["ws"][off:off + B * tiles * groups * 4].view(torch.int32)
+        full_tiles = float(flags.float().mean().item())
+    except Exception:
+        full_tiles = None
+
     clocks = sampler.stop(t_load0, t_load1) if rank == 0 else None
     if errs:
         raise RuntimeError(f"C-ABI calls failed: {errs[:3]}")
@@ -512,7 +525,7 @@ def run_ours(a):
                               "frac": b_eval * B / ((t_cand + t_sel) * 1e-3) / 1e9 / peak},
                 "step": {"achieved_gbs": (b_train + b_eval) * B / (ms_per_step * 1e-3) / 1e9,
                          "frac": (b_train + b_eval) * B / (ms_per_step * 1e-3) / 1e9 / peak}},
-            "e2e": e2e, "clocks": clocks, "epoch_end_ms": epoch_end_ms,
+            "e2e": e2e, "clocks": clocks, "epoch_end_ms": epoch_end_ms, "tiles_listed_in_full": full_tiles,
             "map_report": {k: report[k] for k in ("avg_mAP", "mAP_50")},
         }
         if world == 1 and not a.no_cpu_baseline:

@@ -25,6 +25,8 @@
 //     CPU kernel op for op (offset boxes, ratio vs DOUBLE threshold).  The reference's candidate index of
 //     each survivor (its rank among all keys of the image) is rebuilt from per-chunk counts + a count inside
 //     its own chunk.  The kept detections then go through the fp64 COCO matching while still in shared memory.
+#include <stdlib.h>
+
 #include "kodb_common.cuh"
 
 namespace kodb {
@@ -1910,6 +1912,12 @@ extern "C" int kodb_eval_tail(const kodb_head_level* heads_h, const kodb_level_c
     p.ns = (tiles + p.sample_stride - 1) / p.sample_stride;
     p.magic_b = magic_div((unsigned)batch, (uint64_t)tiles * batch + CW_WARPS);
     p.magic_s1 = p.sample_stride > 1 ? magic_div((unsigned)(p.sample_stride - 1), (uint64_t)tiles) : 0u;
+    static bool env_read = false;
+    if (!env_read) {  // tuning knob (like KODB_TRAIN_DENSE_PER_SM); the debug hook overrides it
+        env_read = true;
+        const char* e = getenv("KODB_HOT_TARGET");
+        if (e && atoi(e) > 0) g_hot_target = atoi(e);
+    }
     p.hot_target = g_hot_target;
     if (p.chunks_per_image > CHUNK_CAP) return KODB_ERR_UNSUPPORTED;
     if ((rc = carve_ws(p, workspace, workspace_bytes)) != KODB_OK) return rc;
