@@ -8,23 +8,24 @@
 //                     PyCOCOMAPEvalCallback drives (pycoco_map_eval.py:50-106), on the kept detections.
 //
 // Two kernels per call:
-//  1. cand_kernel (grid = tiles x images; a tile = up to 1024 contiguous cells of one (level, anchor) plane):
-//     each thread owns 4 consecutive cells and streams the obj plane and the C class planes with float4
-//     loads (issued in batches before use), keeps the (cell, class) pairs with obj > thr and obj*cls > thr
-//     (nms.py:33-48) as 16-bit ids in shared memory, then the whole CTA writes them – balanced, one pair
-//     per thread – as (score, key = row*C + class) into ONE contiguous chunk of the image's candidate
-//     arrays (one global atomicAdd per chunk).  Chunks and the entries inside a chunk land in arbitrary
-//     order: order is re-established later from the keys.  A 512-bin score histogram per image is
-//     accumulated on the side.  Boxes are NOT decoded here.
-//  2. select_nms_kernel (one 1024-thread CTA per image): exact extraction of the next-best batch in
-//     (score desc, key asc) order – cut taken from the coarse histogram; if one bin overflows the sort
-//     capacity (ties, skewed scores) it is refined by a radix-select over the 64-bit composite key –
-//     shuffle/shared-memory bitonic sort of the batch, box decode for the batch only, greedy NMS in
-//     sub-blocks of 32 with warp-ballot suppression masks against the kept list, early exit at max_det keeps
-//     (exact: the first 300 keeps depend only on the scanned prefix).  fp32 IoU arithmetic is torchvision's
-//     CPU kernel op for op (offset boxes, ratio vs DOUBLE threshold).  The reference's candidate index of
-//     each survivor (its rank among all keys of the image) is rebuilt from per-chunk counts + a count inside
-//     its own chunk.  The kept detections then go through the fp64 COCO matching while still in shared memory.
+//  1. Candidates.  Fused path (planar head, planes divisible into float4): cand_floor_kernel, one WARP per tile of
+//     128 cells of one (level, anchor) plane -- see the comment in front of it: the complete candidate set
+//     (obj > thr and obj*cls > thr, nms.py:33-48) goes into 16-bit class masks, and only the candidates at or above
+//     a per-image score floor (measured by the image's sample CTA) are listed as (score, key = row*C + class).
+//     Decoded (B, N, 5+C) input (kodb_nms) and odd grids: cand_kernel, one thread per row / cell, lists everything.
+//     Chunks and the entries inside a chunk land in arbitrary order: order is re-established later from the keys.
+//     A 512-bin score histogram per image is accumulated on the side.  Boxes are NOT decoded here.
+//  2. select_nms_kernel (one 512-thread CTA per image, two per SM): exact extraction of the next-best batch in
+//     (score desc, key asc) order -- cut taken from the coarse histogram (restricted to the bins the list is complete
+//     for); if one bin overflows the sort capacity (ties, skewed scores) it is refined by a radix-select over the
+//     64-bit composite key -- candidates collected straight into per-bin segments and ordered by counting (bitonic
+//     fallback), box decode for the batch only, class-bucketed greedy NMS with bit-mask tiles (generic 64-wide step
+//     path when classes could interact), early exit at max_det keeps (exact: the first 300 keeps depend only on the
+//     scanned prefix).  fp32 IoU arithmetic is torchvision's CPU kernel op for op (offset boxes, ratio vs DOUBLE
+//     threshold).  The reference's candidate index of each survivor (its rank among all keys of the image) is rebuilt
+//     from per-tile counts + the class masks (fused path) or a count inside its own chunk.  If the list runs dry
+//     before max_det survivors, a completion pass lists the rest of the image from the masks.  The kept detections
+//     then go through the fp64 COCO matching while still in shared memory.
 #include <stdlib.h>
 
 #include "kodb_common.cuh"
