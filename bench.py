@@ -460,7 +460,7 @@ def run_ours(a):
         al = lambda v: (v + 255) // 256 * 256
         off = al(B * 4) + al(B * 512 * 4) + al(B * 4)
         flags = sets[0]["ws"][off:off + B * tiles * groups * 4].view(torch.int32)
-        full_tiles = float(flags.float().mean().item())
+        full_tiles = float((flags == 511).float().mean().item())  # chunk floor HB - 1: listed with no floor
     except Exception:
         full_tiles = None
 

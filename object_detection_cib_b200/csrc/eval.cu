@@ -77,6 +77,8 @@ struct EvalParams {
     int ns, sample_stride;     // sample tiles per image: tiles 0, S, 2S, ... (one per warp of the image's sample CTA)
     unsigned magic_b, magic_s1; // ceil(2^32 / B), ceil(2^32 / (S - 1)) when exact over the grid's index range, else 0
     int hot_target;            // estimated number of listed candidates per image the floor aims at
+    int floor_polls;           // bounded wait (x100 ns) for the floor at a tile's second chance; 0 in production (no gain
+                               // measured on B200), large in the tests that must exercise floors on small batches
     int* floor_word;           // [B]  (floor bin + 1), 0 = not published yet; zero on entry / exit
     unsigned short* mask;      // [B][ngroups][rows]  bit u: class 16*group + u of the row is a candidate
     int64_t mask_stride;       // elements per image
@@ -369,7 +371,6 @@ __device__ __forceinline__ unsigned long long expand_nibbles(unsigned a16) {  //
 }
 
 constexpr int HOT_TARGET = 2048;
-constexpr int FLOOR_POLLS = 0;      // optional bounded wait for the floor at the second chance (measured: no gain on B200)
 
 // smallest positive score of coarse bin d (d < HB - 1)
 __device__ __forceinline__ float coarse_lower_edge(int d) { return __uint_as_float(((0x3F800000u >> 18) - (uint32_t)d) << 18); }
@@ -607,7 +608,7 @@ __global__ void __launch_bounds__(CW_WARPS * 32, 3) cand_floor_kernel(const __gr
             if (lane == 0) {
                 const volatile int* fw = p.floor_word + b;
                 w = *fw;
-                for (int tries = 0; w == 0 && tries < FLOOR_POLLS; ++tries) {
+                for (int tries = 0; w == 0 && tries < p.floor_polls; ++tries) {
                     __nanosleep(100);
                     w = *fw;
                 }
@@ -653,7 +654,7 @@ __global__ void __launch_bounds__(CW_WARPS * 32, 3) cand_floor_kernel(const __gr
         if (lane == 0) {
             const int64_t chunk = (int64_t)b * p.chunks_per_image + (int64_t)t * p.ngroups + grp;
             p.chunk_count[chunk] = n_pass;
-            p.chunk_start[chunk] = full ? 1 : 0;  // chunk flag: listed in full
+            p.chunk_start[chunk] = full ? HB - 1 : floor_bin;  // the floor this chunk was listed with (HB - 1: everything)
         }
         // pairs to list; the space is claimed now and the reply of the atomic is only needed after the id list is built
         const int hot = __popc(hm[0]) + __popc(hm[1]) + __popc(hm[2]) + __popc(hm[3]);
@@ -945,7 +946,7 @@ __device__ void match_image(MatchSmem& ms, GtSmem& gs, int nk, int C, int ng, co
 // Four warps, one tile at a time each; scratch on top of the batch arrays (free between batches).  Block-wide.
 __device__ unsigned int g_completions = 0u;  // debug statistic: completion passes since the last query
 
-__device__ int complete_list(const EvalParams& p, NmsSmem& s, int b, int n0, int floor_bin) {
+__device__ int complete_list(const EvalParams& p, NmsSmem& s, int b, int n0) {
     constexpr int CL_WARPS = 4;
     if (threadIdx.x == 0) atomicAdd(&g_completions, 1u);
     static_assert(sizeof(s.pm) >= CL_WARPS * WT_CELLS * CGROUP * sizeof(unsigned short), "id lists fit in pm");
@@ -970,7 +971,8 @@ __device__ int complete_list(const EvalParams& p, NmsSmem& s, int b, int n0, int
             const float* cls_base = hd.cls + (int64_t)b * hd.cls_sb + (int64_t)a * hd.cls_sa + c0;
             for (int i = lane; i < ncell; i += 32) so[i] = sigmoid_eval(obj_base[i]);
             for (int g = 0; g < p.ngroups; ++g) {
-                if (flags[g]) continue;  // this chunk is listed in full already
+                const int floor_bin = flags[g];  // the floor the candidate kernel listed this chunk with
+                if (floor_bin >= HB - 1) continue;  // listed in full already
                 const int j0 = g * CGROUP;
                 const unsigned short* mk = mask_img + (int64_t)g * p.rows + row0;
                 int mine = 0;
@@ -1045,7 +1047,9 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) select_nms_kernel(const __grid
     int n = p.img_count[b];  // listed candidates (floor mode: a subset of all candidates until the completion pass)
     const int hist_v = tid < HB ? p.hist[(int64_t)b * HB + tid] : 0;
     const int cc0 = tid < p.chunks_per_image ? ccount[tid] : 0;
-    const int floor_w = floor_mode ? p.floor_word[b] : 0;
+    int cfloor = HB - 1;  // floor mode: the lowest-numbered floor bin any chunk of the image was listed with
+    if (floor_mode)
+        for (int t = tid; t < p.chunks_per_image; t += NMS_THREADS) cfloor = min(cfloor, cstart[t]);
     int g0 = 0, gt_n = 0;
     if (p.do_match) {
         g0 = p.gt_offsets[b];
@@ -1104,11 +1108,18 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) select_nms_kernel(const __grid
     const bool rank_mode = n_total > p.cfg.max_nms;  // nms.py:61-63: candidates re-ordered by confidence, top max_nms kept
     const int limit = rank_mode ? p.cfg.max_nms : n_total;
     // floor mode: bins 0..avail-1 of the histogram are complete (every candidate of those bins is listed)
+    // Every chunk records the floor it was listed with (a tile that ran before the floor was published lists
+    // everything), so the complete bins follow from the chunks themselves, whatever the timing was.
     int avail = HB;
-    int floor_bin = HB - 1;
     if (floor_mode) {
-        floor_bin = floor_w - 1;
-        avail = floor_bin >= HB - 1 ? HB : floor_bin + 1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cfloor = min(cfloor, __shfl_xor_sync(KODB_FULL_MASK, cfloor, o));
+        if (lane == 0) s.scan_tmp[wid] = cfloor;  // (free between the scans above and the cut below)
+        __syncthreads();
+        cfloor = s.scan_tmp[lane < NMS_THREADS / 32 ? lane : 0];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cfloor = min(cfloor, __shfl_xor_sync(KODB_FULL_MASK, cfloor, o));
+        avail = cfloor >= HB - 1 ? HB : cfloor + 1;
         if (tid == 0) p.floor_word[b] = 0;  // reusable without a memset
     }
     if (p.do_match) {  // (GT_CAP == NMS_THREADS: one ground-truth box per thread)
@@ -1143,7 +1154,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) select_nms_kernel(const __grid
             if (total == 0) {
                 if (avail == HB) break;  // nothing left
                 // the listed candidates ran dry before max_det survivors: list the rest of the image from the masks
-                n = complete_list(p, s, b, n, floor_bin);
+                n = complete_list(p, s, b, n);
                 avail = HB;
                 continue;
             }
@@ -1836,6 +1847,7 @@ static int setup_match(EvalParams& p, const kodb_targets* gt, const kodb_match_o
 
 static long long* g_trace = nullptr;
 static int g_hot_target = HOT_TARGET;
+static int g_floor_polls = 0;
 
 // m = ceil(2^32 / d) with umulhi(n, m) == n / d for every n <= n_max, or 0 if that does not hold
 static unsigned magic_div(unsigned d, uint64_t n_max) {
@@ -1876,6 +1888,9 @@ extern "C" int kodb_debug_take_completions(void) {
     cudaMemcpyToSymbol(kodb::g_completions, &z, sizeof(z));
     return (int)v;
 }
+// debug hook: let every tile wait (bounded, n x 100 ns) for its image's floor instead of listing everything when it
+// comes first -- makes small test batches use the floors deterministically.  0 restores the default.
+extern "C" void kodb_debug_set_floor_polls(int n) { kodb::g_floor_polls = n > 0 ? n : 0; }
 extern "C" void kodb_debug_set_hot_target(int n) { kodb::g_hot_target = n > 0 ? n : kodb::HOT_TARGET; }
 
 extern "C" int64_t kodb_eval_workspace_bytes(int32_t batch, int64_t rows_per_image, int32_t num_classes) {
@@ -1920,6 +1935,7 @@ extern "C" int kodb_eval_tail(const kodb_head_level* heads_h, const kodb_level_c
         if (e && atoi(e) > 0) g_hot_target = atoi(e);
     }
     p.hot_target = g_hot_target;
+    p.floor_polls = g_floor_polls;
     if (p.chunks_per_image > CHUNK_CAP) return KODB_ERR_UNSUPPORTED;
     if ((rc = carve_ws(p, workspace, workspace_bytes)) != KODB_OK) return rc;
     if ((rc = setup_match(p, gt_h, match_h)) != KODB_OK) return rc;
@@ -1967,6 +1983,7 @@ extern "C" int kodb_nms(const float* detections, int32_t batch, int64_t rows, co
     p.sample_stride = 1;
     p.magic_b = p.magic_s1 = 0u;
     p.hot_target = 0;
+    p.floor_polls = 0;
     if (p.chunks_per_image > CHUNK_CAP) return KODB_ERR_UNSUPPORTED;
     if ((rc = carve_ws(p, workspace, workspace_bytes)) != KODB_OK) return rc;
     if ((rc = setup_match(p, gt_h, match_h)) != KODB_OK) return rc;

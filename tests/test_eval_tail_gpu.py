@@ -169,12 +169,14 @@ def test_fused_floor_completion(target, B, S, C, shift, oracle_lib):
     want = N.nms_padded(N.get_detections(shape, dh, info), 0.001, 0.6)
     lib = L.lib()
     lib.kodb_debug_set_hot_target(int(target))
+    lib.kodb_debug_set_floor_polls(200000)  # every tile waits (bounded) for its floor: a small batch is one wave
     lib.kodb_debug_take_completions()
     try:
         got = N.eval_tail(shape, dh, info, 0.001, 0.6)
         torch.cuda.synchronize()
     finally:
         lib.kodb_debug_set_hot_target(0)
+        lib.kodb_debug_set_floor_polls(0)
     completions = lib.kodb_debug_take_completions()
     if target <= 64:
         assert completions > 0, "a floor this high must force the completion pass"
@@ -209,11 +211,13 @@ def test_fused_fuzz(B, S, C, conf, iou, shift, target, oracle_lib):
     two_step = N.nms_padded(det, conf, iou)
     lib = L.lib()
     lib.kodb_debug_set_hot_target(int(target))
+    lib.kodb_debug_set_floor_polls(200000 if target else 0)
     try:
         fused = N.eval_tail(shape, dh, info, conf, iou)
         torch.cuda.synchronize()
     finally:
         lib.kodb_debug_set_hot_target(0)
+        lib.kodb_debug_set_floor_polls(0)
     assert torch.equal(fused.counts, two_step.counts)
     assert torch.equal(fused.dets, two_step.dets) and torch.equal(fused.keep_idx, two_step.keep_idx)
     assert torch.equal(fused.num_candidates, two_step.num_candidates)
