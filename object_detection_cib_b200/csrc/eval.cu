@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(CAND_THREADS) cand_kernel(const __grid_constan
 // would produce.  Flagged pairs become 16-bit ids in a warp-private shared list, then the warp writes them --
 // balanced, one pair per lane -- as (score, key) into one contiguous chunk claimed with a single atomicAdd.
 constexpr int WT_CELLS = 128;
-constexpr int CW_WARPS = 8;
+constexpr int CW_WARPS = 4;   // 128-thread CTAs (32 KB smem at 10 classes): pack next to the select kernel's 100 KB CTAs
 constexpr float TAU_WINDOW = 2.0e-4f;  // >> the ~1.5e-5 combined error of tau and of the fp32 product for thr/o < 0.9
 
 __device__ __forceinline__ unsigned long long expand_nibbles(unsigned a16) {  // bit u -> bits 4u..4u+3
@@ -412,7 +412,7 @@ __device__ __forceinline__ unsigned fix_borderline(unsigned cmv, unsigned border
 }
 
 template <int NQ>
-__global__ void __launch_bounds__(CW_WARPS * 32, 3) cand_floor_kernel(const __grid_constant__ EvalParams p) {
+__global__ void __launch_bounds__(CW_WARPS * 32, 6) cand_floor_kernel(const __grid_constant__ EvalParams p) {
     extern __shared__ __align__(16) unsigned char cw_smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     CandWarpSmem<NQ>& sm = reinterpret_cast<CandWarpSmem<NQ>*>(cw_smem_raw)[wid];
