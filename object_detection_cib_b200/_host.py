@@ -143,6 +143,27 @@ def pack_targets(targets: Sequence, device) -> PackedTargets:
     cxcywh + 1/stride arithmetic exactly like the reference's assignment into its fp32 buffer
     (yv5.py:92-113).  Host tensors go through ONE pinned staging buffer and one H2D copy."""
     device = torch.device(device)
+    from .data import HostPackedTargets  # (data.py imports nothing from this module)
+
+    if isinstance(targets, HostPackedTargets):
+        # collated in the DataLoader (data.packed_collate_fn): ONE H2D copy of the (pinned) blob, nothing to pack
+        hp = targets
+        T, B = hp.num_targets, len(hp)
+        dblob = hp.blob.to(device, non_blocking=True)
+        bsz = 8 if hp.f64 else 4
+        bdt = torch.float64 if hp.f64 else torch.float32
+        boxes = dblob[:T * 4 * bsz].view(bdt).view(T, 4)
+        labels = dblob[hp.nb_boxes:hp.nb_boxes + T * 8].view(torch.long)
+        offsets = dblob[hp.nb_boxes + hp.nb_labels:hp.nb_boxes + hp.nb_labels + (B + 1) * 4].view(torch.int32)
+        s = L.Targets()
+        s.boxes = boxes.data_ptr() if T else 0
+        s.labels = labels.data_ptr() if T else 0
+        s.img_offsets = offsets.data_ptr()
+        s.boxes_dtype = L.BOXES_F64 if hp.f64 else L.BOXES_F32
+        s.num_targets = T
+        s.batch = B
+        s.max_per_image = max(hp.counts) if hp.counts else 0
+        return PackedTargets(s, (boxes, labels, offsets, dblob), T, B, s.max_per_image, list(hp.counts))
     B = len(targets)
     counts = [int(t[0].shape[0]) if t[0].dim() > 0 and t[0].numel() else 0 for t in targets]
     T = sum(counts)

@@ -60,3 +60,52 @@ def test_struct_sizes_match_the_header():
 def test_cpu_tensors_are_refused():
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         N.nms_padded(torch.zeros(1, 10, 15))
+
+
+def test_packed_collate_matches_the_reference_collate():
+    """data.packed_collate_fn returns the reference's triple; the targets object is a
+    Sequence[DetectionTarget] whose items equal the inputs, for fp32, fp64, empty and (0,)-shaped targets."""
+    from object_detection_cib_b200.data import HostPackedTargets, packed_collate_fn
+    from object_detection_cib_b200.types import DetectionTarget
+    g = torch.Generator().manual_seed(3)
+    targets = []
+    for n in (3, 0, 7, 1):
+        b = torch.rand(n, 4, generator=g) * 600
+        targets.append(DetectionTarget(torch.cat([b[:, :2], b[:, :2] + 10 + b[:, 2:] / 6], 1), torch.randint(0, 10, (n,), generator=g)))
+    targets[1] = DetectionTarget(torch.zeros(0), torch.zeros(0, dtype=torch.long))  # sample_reader.py:133 shape
+    batch = [(torch.full((3, 8, 8), float(i)), t, ("p%d" % i, (8, 8))) for i, t in enumerate(targets)]
+    imgs, packed, info = packed_collate_fn(batch)
+    assert imgs.shape == (4, 3, 8, 8) and info[2][0] == "p2"
+    assert isinstance(packed, HostPackedTargets) and len(packed) == 4 and packed.num_targets == 11
+    assert packed.offsets.tolist() == [0, 3, 3, 10, 11] and not packed.f64
+    for got, want in zip(packed, targets):
+        assert torch.equal(got.boxes, want.boxes.reshape(-1, 4)) and torch.equal(got.labels, want.labels.reshape(-1))
+    assert torch.equal(packed[-1].labels, targets[3].labels)
+    # fp64 boxes of ONE image make the blob fp64 (the kernels convert after the cxcywh + 1/stride arithmetic)
+    t64 = list(targets)
+    t64[2] = DetectionTarget(targets[2].boxes.double() + 1e-9, targets[2].labels)
+    p64 = HostPackedTargets.from_targets(t64)
+    assert p64.f64 and p64.boxes.dtype == torch.float64 and torch.equal(p64[2].boxes, t64[2].boxes)
+    assert torch.equal(p64[0].boxes, targets[0].boxes.double())
+    # an all-empty batch
+    pe = HostPackedTargets.from_targets([targets[1], targets[1]])
+    assert len(pe) == 2 and pe.num_targets == 0 and pe.offsets.tolist() == [0, 0, 0]
+
+
+def test_packed_targets_work_with_a_dataloader():
+    from object_detection_cib_b200.data import HostPackedTargets, packed_collate_fn
+    from object_detection_cib_b200.types import DetectionTarget
+
+    class DS(torch.utils.data.Dataset):
+        def __len__(self):
+            return 6
+
+        def __getitem__(self, i):
+            n = i % 3
+            return torch.zeros(3, 4, 4), DetectionTarget(torch.full((n, 4), float(i)), torch.full((n,), i, dtype=torch.long)), None
+
+    dl = torch.utils.data.DataLoader(DS(), batch_size=3, collate_fn=packed_collate_fn, num_workers=0)
+    batches = list(dl)
+    assert len(batches) == 2
+    _, t, _ = batches[1]
+    assert isinstance(t, HostPackedTargets) and t.counts == [0, 1, 2] and float(t[2].boxes[0, 0]) == 5.0

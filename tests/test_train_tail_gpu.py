@@ -132,3 +132,31 @@ def test_fails_loudly_on_cpu_tensors():
     mod = _loss_module(Yolov5LossParams.get_default(), "ciou", None)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         mod(FeatureShape(64, 64), heads, syn.make_targets(1, 64, 3))
+
+
+def test_collated_targets_equal_the_tuple_form():
+    """data.packed_collate_fn's HostPackedTargets (one pinned blob, one H2D) drives the loss and the eval tail to the
+    same bits as the reference's tuple of DetectionTarget."""
+    from object_detection_cib_b200 import nms as N
+    from object_detection_cib_b200.data import HostPackedTargets
+    from object_detection_cib_b200.map_eval import DeviceCocoMapEvaluator
+    B, S, C = 5, 320, 10
+    heads = syn.make_head(B, S, C, seed=21)
+    targets = syn.make_targets(B, S, C, seed=21, n_min=0, n_max=9, empty_images=(3,))
+    packed = HostPackedTargets.from_targets(targets).pin_memory()
+    assert packed.blob.is_pinned()
+    info, shape = default_anchor_info(), FeatureShape(S, S)
+    loss = Yolov5Loss(Yolov5LabelAssigner(info), Yolov5LossParams.get_default(), IoUCalculator(IoUType.ciou), syn.readme_class_weights())
+    out = []
+    for tg in (targets, packed):
+        leaves = [DetectionHeadResult(*[t.to(DEV).requires_grad_(True) for t in lv]) for lv in heads]
+        r = loss(shape, leaves, tg)
+        (r.localization + r.classification + r.objectness).backward()
+        ev = DeviceCocoMapEvaluator(C, device=DEV)
+        res, rec = N.eval_tail(shape, [DetectionHeadResult(*[t.detach() for t in lv]) for lv in leaves], info, 0.001, 0.6,
+                               targets=tg, gt_count=ev.gt_count)
+        out.append((torch.stack(list(r)).detach(), [t.grad for lv in leaves for t in lv], rec.tp.clone(), ev.gt_count.clone()))
+    assert torch.equal(out[0][0], out[1][0])
+    for ga, gb in zip(out[0][1], out[1][1]):
+        assert torch.equal(ga, gb)
+    assert torch.equal(out[0][2], out[1][2]) and torch.equal(out[0][3], out[1][3])
