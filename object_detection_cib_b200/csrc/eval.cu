@@ -1759,7 +1759,7 @@ static int plan_geom(EvalGeom& g, const kodb_head_level* heads_h, const kodb_lev
     }
     (void)C;
     int rows = 0, tiles = 0;
-    const int cap = vec == 4 ? WT_CELLS : CAND_THREADS;  // warp tiles (cand_warp_kernel) / block tiles (cand_kernel<.,1>)
+    const int cap = vec == 4 ? WT_CELLS : CAND_THREADS;  // warp tiles (cand_floor_kernel) / block tiles (cand_kernel<.,1>)
     for (int l = 0; l < KODB_NUM_LEVELS; ++l) {
         g.head[l] = heads_h[l];
         g.lv[l] = levels_h[l];
