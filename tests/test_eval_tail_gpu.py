@@ -193,6 +193,7 @@ _FUZZ = [
     (2, 640, 10, 0.25, 0.45, 4.0, 0), (5, 320, 10, 0.001, 0.6, 0.0, 50), (2, 512, 33, 0.001, 0.5, 2.0, 200),
     (1, 640, 80, 0.001, 0.6, 2.0, 0), (4, 352, 10, 0.001, 0.6, 5.0, 0), (2, 640, 16, 0.05, 0.7, 3.0, 30),
     (3, 384, 2, 0.001, 0.6, 6.0, 0), (2, 448, 10, 0.001, 0.0, 2.0, 0), (1, 640, 10, 0.001, 0.6, 8.0, 0),
+    (1, 320, 3, 0.0, 0.6, 2.0, 0), (2, 320, 10, 0.0, 0.6, 3.0, 100), (2, 640, 10, 0.9, 0.6, 9.0, 0),
 ]
 
 
