@@ -77,6 +77,7 @@ struct EvalParams {
     int ns, sample_stride;     // sample tiles per image: tiles 0, S, 2S, ... (one per warp of the image's sample CTA)
     unsigned magic_b, magic_s1; // ceil(2^32 / B), ceil(2^32 / (S - 1)) when exact over the grid's index range, else 0
     int hot_target;            // estimated number of listed candidates per image the floor aims at
+    int l2_stream;             // class planes are loaded with the L2 evict-first policy (tuning knob KODB_EVAL_L2_STREAM)
     int floor_polls;           // bounded wait (x100 ns) for the floor at a tile's second chance; 0 in production (no gain
                                // measured on B200), large in the tests that must exercise floors on small batches
     int* floor_word;           // [B]  (floor bin + 1), 0 = not published yet; zero on entry / exit
@@ -165,7 +166,8 @@ __device__ __forceinline__ float4 fetch_box(const EvalParams& p, int b, int row)
     const kodb_head_level& hd = p.g.head[L];
     const int gy = cell / lv.W, gx = cell - gy * lv.W;
     const int64_t bo = (int64_t)b * hd.box_sb + (int64_t)a * hd.box_sa + cell;
-    return decode_box(hd.box[bo], hd.box[bo + hd.box_sp], hd.box[bo + 2 * hd.box_sp], hd.box[bo + 3 * hd.box_sp], (float)gx,
+    return decode_box(__ldcs(hd.box + bo), __ldcs(hd.box + bo + hd.box_sp), __ldcs(hd.box + bo + 2 * hd.box_sp),
+                      __ldcs(hd.box + bo + 3 * hd.box_sp), (float)gx,
                       (float)gy, (float)lv.stride, lv.anchor_px[a][0], lv.anchor_px[a][1]);
 }
 
@@ -460,14 +462,15 @@ __global__ void __launch_bounds__(CW_WARPS * 32, 6) cand_floor_kernel(const __gr
     // at once without holding registers, so three CTAs fit on an SM.  The obj logits land in sm.o and are replaced
     // by their sigmoid below.
     const unsigned sq0 = (unsigned)__cvta_generic_to_shared(&sm.q[0][cell0]);  // class u of the stash: + u * 512 bytes
-    if (in_range) cp_async16(&sm.o[cell0], obj_base + cell0);
+    const unsigned long long l2pol = l2_evict_first_policy(p.l2_stream != 0);
+    if (in_range) cp_async16(&sm.o[cell0], obj_base + cell0);  // (normal policy: the loss reads the obj planes too)
     else *reinterpret_cast<float4*>(&sm.o[cell0]) = zero4;
     {
         const int nld = in_range ? min(C, CGROUP) : 0;
         const float* cp = cls_base + cell0;
 #pragma unroll
         for (int u = 0; u < NQ; ++u) {
-            if (u < nld) cp_async16_s(sq0 + u * (WT_CELLS * 4), cp);
+            if (u < nld) cp_async16_s_ef(sq0 + u * (WT_CELLS * 4), cp, l2pol);
             else *reinterpret_cast<float4*>(&sm.q[u][cell0]) = zero4;
             cp += cls_step;
         }
@@ -533,7 +536,7 @@ __global__ void __launch_bounds__(CW_WARPS * 32, 6) cand_floor_kernel(const __gr
             const int nld = in_range ? jn : 0;
 #pragma unroll
             for (int u = 0; u < NQ; ++u) {
-                if (u < nld) cp_async16_s(sq0 + u * (WT_CELLS * 4), cp);
+                if (u < nld) cp_async16_s_ef(sq0 + u * (WT_CELLS * 4), cp, l2pol);
                 else *reinterpret_cast<float4*>(&sm.q[u][cell0]) = zero4;
                 cp += cls_step;
             }
@@ -1848,6 +1851,7 @@ static int setup_match(EvalParams& p, const kodb_targets* gt, const kodb_match_o
 static long long* g_trace = nullptr;
 static int g_hot_target = HOT_TARGET;
 static int g_floor_polls = 0;
+static int g_l2_stream = 1;
 
 // m = ceil(2^32 / d) with umulhi(n, m) == n / d for every n <= n_max, or 0 if that does not hold
 static unsigned magic_div(unsigned d, uint64_t n_max) {
@@ -1933,9 +1937,12 @@ extern "C" int kodb_eval_tail(const kodb_head_level* heads_h, const kodb_level_c
         env_read = true;
         const char* e = getenv("KODB_HOT_TARGET");
         if (e && atoi(e) > 0) g_hot_target = atoi(e);
+        e = getenv("KODB_EVAL_L2_STREAM");
+        if (e) g_l2_stream = atoi(e) != 0;
     }
     p.hot_target = g_hot_target;
     p.floor_polls = g_floor_polls;
+    p.l2_stream = g_l2_stream;
     if (p.chunks_per_image > CHUNK_CAP) return KODB_ERR_UNSUPPORTED;
     if ((rc = carve_ws(p, workspace, workspace_bytes)) != KODB_OK) return rc;
     if ((rc = setup_match(p, gt_h, match_h)) != KODB_OK) return rc;
@@ -1984,6 +1991,7 @@ extern "C" int kodb_nms(const float* detections, int32_t batch, int64_t rows, co
     p.magic_b = p.magic_s1 = 0u;
     p.hot_target = 0;
     p.floor_polls = 0;
+    p.l2_stream = 0;
     if (p.chunks_per_image > CHUNK_CAP) return KODB_ERR_UNSUPPORTED;
     if ((rc = carve_ws(p, workspace, workspace_bytes)) != KODB_OK) return rc;
     if ((rc = setup_match(p, gt_h, match_h)) != KODB_OK) return rc;

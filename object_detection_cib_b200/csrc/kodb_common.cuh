@@ -174,6 +174,17 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async16_s(unsigned smem_dst, const void* gmem_src) {  // shared-window address
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
 }
+// streaming variant: the source is read once, so its L2 lines are the first to go (keeps what other kernels of the
+// pipeline still need -- candidate lists, class masks -- in the L2)
+__device__ __forceinline__ unsigned long long l2_evict_first_policy(bool streaming = true) {
+    unsigned long long pol;
+    if (streaming) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void cp_async16_s_ef(unsigned smem_dst, const void* gmem_src, unsigned long long pol) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
