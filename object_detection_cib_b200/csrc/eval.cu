@@ -26,6 +26,7 @@
 //     from per-tile counts + the class masks (fused path) or a count inside its own chunk.  If the list runs dry
 //     before max_det survivors, a completion pass lists the rest of the image from the masks.  The kept detections
 //     then go through the fp64 COCO matching while still in shared memory.
+#include <stddef.h>
 #include <stdlib.h>
 
 #include "kodb_common.cuh"
@@ -781,6 +782,8 @@ struct NmsSmem {
     int ccount[KODB_MAX_CLASSES], cbase[KODB_MAX_CLASSES], tstart[KODB_MAX_CLASSES + 1];
     float kx1[MAX_DET_CAP], ky1[MAX_DET_CAP], kx2[MAX_DET_CAP], ky2[MAX_DET_CAP], karea[MAX_DET_CAP];
     int kcls[MAX_DET_CAP];
+    int kc_cnt[KODB_MAX_CLASSES], kc_base[KODB_MAX_CLASSES];  // survivors bucketed by class (rebuilt per batch) ...
+    unsigned short kc_idx[MAX_DET_CAP];                        // ... so a candidate is only tested against its own class
     unsigned long long kept_ck[MAX_DET_CAP];
     long long kept_idx[MAX_DET_CAP];
     int scan_tmp[33];
@@ -950,51 +953,64 @@ __device__ void match_image(MatchSmem& ms, GtSmem& gs, int nk, int C, int ng, co
 __device__ unsigned int g_completions = 0u;  // debug statistic: completion passes since the last query
 
 __device__ int complete_list(const EvalParams& p, NmsSmem& s, int b, int n0) {
-    constexpr int CL_WARPS = 4;
+    // every warp of the CTA takes half tiles (64 cells, two per lane); scratch = the batch arrays bx1 .. pm, which are
+    // consecutive members of NmsSmem and free between batches
+    constexpr int HALF = WT_CELLS / 2;
+    constexpr int CL_WARPS = NMS_THREADS / 32;
+    constexpr size_t PER_WARP = HALF * CGROUP * sizeof(unsigned short) + HALF * sizeof(float);
+    static_assert(offsetof(NmsSmem, pm) + sizeof(s.pm) - offsetof(NmsSmem, bx1) >= CL_WARPS * PER_WARP, "scratch of the completion pass");
+    static_assert(offsetof(NmsSmem, bx1) < offsetof(NmsSmem, pm) && offsetof(NmsSmem, bx1) % 16 == 0, "batch arrays are laid out in order");
     if (threadIdx.x == 0) atomicAdd(&g_completions, 1u);
-    static_assert(sizeof(s.pm) >= CL_WARPS * WT_CELLS * CGROUP * sizeof(unsigned short), "id lists fit in pm");
-    static_assert(sizeof(s.bx1) >= CL_WARPS * WT_CELLS * sizeof(float), "objectness fits in bx1");
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int C = p.C;
     if (tid == 0) s.cnt = 0;
     __syncthreads();
-    if (wid < CL_WARPS) {
-        unsigned short* list = reinterpret_cast<unsigned short*>(s.pm) + wid * (WT_CELLS * CGROUP);
-        float* so = s.bx1 + wid * WT_CELLS;
+    {
+        unsigned char* scratch = reinterpret_cast<unsigned char*>(s.bx1) + (size_t)wid * PER_WARP;
+        float* so = reinterpret_cast<float*>(scratch);
+        unsigned short* list = reinterpret_cast<unsigned short*>(scratch + HALF * sizeof(float));
         float* sc_img = p.cand_score + (int64_t)b * p.cand_stride + n0;
         uint32_t* ky_img = p.cand_key + (int64_t)b * p.cand_stride + n0;
         const unsigned short* mask_img = p.mask + (int64_t)b * p.mask_stride;
-        for (int t = wid; t < p.tiles_per_image; t += CL_WARPS) {
+        for (int unit = wid; unit < 2 * p.tiles_per_image; unit += CL_WARPS) {
+            const int t = unit >> 1, h0 = (unit & 1) * HALF;
             const int* flags = p.chunk_start + (int64_t)b * p.chunks_per_image + (int64_t)t * p.ngroups;
             int L, a, c0, ncell;
             planar_tile(p.g, t, L, a, c0, ncell);
+            if (h0 >= ncell) continue;
+            bool any_cold_chunk = false;
+            for (int g = 0; g < p.ngroups; ++g) any_cold_chunk |= flags[g] < HB - 1;
+            if (!any_cold_chunk) continue;  // every chunk of the tile is listed in full already
             const kodb_head_level& hd = p.g.head[L];
-            const int row0 = p.g.row_base[L] + a * (p.g.lv[L].H * p.g.lv[L].W) + c0;
-            const float* obj_base = hd.obj + (int64_t)b * hd.obj_sb + (int64_t)a * hd.obj_sa + c0;
-            const float* cls_base = hd.cls + (int64_t)b * hd.cls_sb + (int64_t)a * hd.cls_sa + c0;
-            for (int i = lane; i < ncell; i += 32) so[i] = sigmoid_eval(obj_base[i]);
+            const int row0 = p.g.row_base[L] + a * (p.g.lv[L].H * p.g.lv[L].W) + c0 + h0;  // first row of the half tile
+            const int nh = min(HALF, ncell - h0);
+            const float* obj_base = hd.obj + (int64_t)b * hd.obj_sb + (int64_t)a * hd.obj_sa + c0 + h0;
+            const float* cls_base = hd.cls + (int64_t)b * hd.cls_sb + (int64_t)a * hd.cls_sa + c0 + h0;
+            __syncwarp();  // the previous unit's readers of the scratch are done
+            for (int i = lane; i < nh; i += 32) so[i] = sigmoid_eval(obj_base[i]);
             for (int g = 0; g < p.ngroups; ++g) {
                 const int floor_bin = flags[g];  // the floor the candidate kernel listed this chunk with
                 if (floor_bin >= HB - 1) continue;  // listed in full already
                 const int j0 = g * CGROUP;
                 const unsigned short* mk = mask_img + (int64_t)g * p.rows + row0;
                 int mine = 0;
-                unsigned m4[4];
+                unsigned m2[2];
 #pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    const int cl = 4 * lane + v;
-                    m4[v] = cl < ncell ? mk[cl] : 0u;
-                    mine += __popc(m4[v]);
+                for (int v = 0; v < 2; ++v) {
+                    const int cl = 2 * lane + v;
+                    m2[v] = cl < nh ? mk[cl] : 0u;
+                    mine += __popc(m2[v]);
                 }
                 int slot = warp_excl_scan_i(mine, lane);
                 const int n = __shfl_sync(KODB_FULL_MASK, slot + mine, 31);
+                __syncwarp();  // the previous group's readers of the list are done
 #pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    unsigned m = m4[v];
+                for (int v = 0; v < 2; ++v) {
+                    unsigned m = m2[v];
                     while (m) {
                         const int u = __ffs(m) - 1;
                         m &= m - 1;
-                        list[slot++] = (unsigned short)(((4 * lane + v) << 4) | u);
+                        list[slot++] = (unsigned short)(((2 * lane + v) << 4) | u);
                     }
                 }
                 __syncwarp();
@@ -1025,7 +1041,6 @@ __device__ int complete_list(const EvalParams& p, NmsSmem& s, int b, int n0) {
                         }
                     }
                 }
-                __syncwarp();
             }
         }
     }
@@ -1383,6 +1398,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) select_nms_kernel(const __grid
         }
         if (cls_static) {
             for (int i = tid; i < (NMS_THREADS / 32) * C; i += NMS_THREADS) s.hist[i] = 0;  // per-(warp, class) counts
+            if (tid < C) s.kc_cnt[tid] = 0;
         }
         if (__syncthreads_or(bad)) cls_static = false;  // sticky: a kept out-of-window box may reach across classes later
         bool cls_path = cls_static;
@@ -1400,7 +1416,22 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) select_nms_kernel(const __grid
             const unsigned peers = __match_any_sync(KODB_FULL_MASK, my_c);
             const int rank = __popc(peers & ((1u << lane) - 1u));
             if (my_c >= 0 && rank == 0) s.hist[wid * C + my_c] = __popc(peers);
+            int kept_c = 0, kept_r = 0;  // survivors of earlier batches -> per-class lists (unordered inside a class)
+            if (tid < nk) {
+                kept_c = s.kcls[tid];
+                kept_r = atomicAdd(&s.kc_cnt[kept_c], 1);
+            }
             __syncthreads();
+            if (wid == NMS_THREADS / 32 - 1 && nk > 0) {
+                int run = 0;
+                for (int c0 = 0; c0 < C; c0 += 32) {
+                    const int c = c0 + lane;
+                    const int v = c < C ? s.kc_cnt[c] : 0;
+                    const int ex = warp_excl_scan_i(v, lane);
+                    if (c < C) s.kc_base[c] = run + ex;
+                    run += __shfl_sync(KODB_FULL_MASK, ex + v, 31);
+                }
+            }
             for (int c = wid; c < C; c += NMS_THREADS / 32) {  // exclusive prefix over the warps, per class (lane = warp)
                 const int v = lane < NMS_THREADS / 32 ? s.hist[lane * C + c] : 0;
                 const int ex = warp_excl_scan_i(v, lane);
@@ -1408,6 +1439,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) select_nms_kernel(const __grid
                 if (lane == 31) s.ccount[c] = ex + v;
             }
             __syncthreads();
+            if (tid < nk) s.kc_idx[s.kc_base[kept_c] + kept_r] = (unsigned short)tid;
             if (wid == 0) {  // class bases, tile starts, capacity check
                 int run_c = 0, run_t = 0;
                 bool over = false;
@@ -1434,8 +1466,13 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) select_nms_kernel(const __grid
                     s.cbox[my_pos] = make_float4(x1, y1, x2, y2);
                     s.carea[my_pos] = ar;
                     bool dead = false;  // suppressed by a survivor of an earlier batch (same class only)
-                    for (int q = 0; q < nk && !dead; ++q)
-                        dead = s.kcls[q] == my_c && suppresses(s.kx1[q], s.ky1[q], s.kx2[q], s.ky2[q], s.karea[q], x1, y1, x2, y2, ar, iou_thr);
+                    if (nk > 0) {
+                        const int q0 = s.kc_base[my_c], q1 = q0 + s.kc_cnt[my_c];
+                        for (int qi = q0; qi < q1 && !dead; ++qi) {
+                            const int q = s.kc_idx[qi];
+                            dead = suppresses(s.kx1[q], s.ky1[q], s.kx2[q], s.ky2[q], s.karea[q], x1, y1, x2, y2, ar, iou_thr);
+                        }
+                    }
                     s.pre[my_pos] = dead;
                 }
                 __syncthreads();

@@ -126,6 +126,40 @@ def inject_ground_truth(heads: Sequence[HeadLevel], targets, img_size: int, frac
             heads[li].cls[b, ai, gy, gx, int(labels[n])] = 4.0
 
 
+def light_up_neighbourhoods(heads: Sequence[HeadLevel], targets, radius: int = 2, seed: int = 1,
+                            strides: Sequence[int] = STRIDES, anchors_px=ANCHORS_PX) -> None:
+    """Detector-like clutter: every ground-truth box lights up the (2*radius+1)^2 cells around its centre on every
+    anchor that fits it, each decoding to (nearly) the box with high objectness / class confidence.  NMS then has to
+    scan thousands of heavily overlapping candidates for its 300 survivors (several extraction batches, score floors
+    that run dry).  In-place on the head tensors."""
+    gen = torch.Generator()
+    gen.manual_seed(seed)
+    lg = lambda q: math.log(q / (1 - q))
+    for b, (boxes, labels) in enumerate(targets):
+        for n in range(boxes.shape[0]):
+            x1, y1, x2, y2 = (float(v) for v in boxes[n])
+            cx, cy, w, h = (x1 + x2) / 2, (y1 + y2) / 2, max(x2 - x1, 1.0), max(y2 - y1, 1.0)
+            for li, s in enumerate(strides):
+                H, W = heads[li].obj.shape[2], heads[li].obj.shape[3]
+                gx, gy = int(cx / s), int(cy / s)
+                for ai, (aw, ah) in enumerate(anchors_px[li]):
+                    if max(w / aw, aw / w, h / ah, ah / h) >= 4:
+                        continue
+                    sw = min(max(math.sqrt(w / aw) / 2, 1e-3), 1 - 1e-3)
+                    sh = min(max(math.sqrt(h / ah) / 2, 1e-3), 1 - 1e-3)
+                    for dy in range(-radius, radius + 1):
+                        for dx in range(-radius, radius + 1):
+                            yy, xx = gy + dy, gx + dx
+                            if not (0 <= yy < H and 0 <= xx < W):
+                                continue
+                            sx = min(max((cx / s - xx + 0.5) / 2, 0.02), 0.98)
+                            sy = min(max((cy / s - yy + 0.5) / 2, 0.02), 0.98)
+                            dev = heads[li].box.device
+                            heads[li].box[b, ai, yy, xx, :] = torch.tensor([lg(sx), lg(sy), lg(sw), lg(sh)], device=dev)
+                            heads[li].obj[b, ai, yy, xx, 0] = 3.0 - 0.5 * (abs(dx) + abs(dy)) + 0.3 * float(torch.randn(1, generator=gen))
+                            heads[li].cls[b, ai, yy, xx, int(labels[n])] = 3.0 + 0.3 * float(torch.randn(1, generator=gen))
+
+
 def readme_class_weights() -> list[float]:
     """`sum(n)/n_c` in fp32 (kod/lightning/tasks/trainer.py:54-60) for the README instance counts."""
     w = torch.tensor(README_INSTANCE_COUNTS, dtype=torch.float32)

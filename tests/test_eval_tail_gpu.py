@@ -229,6 +229,25 @@ def test_fused_fuzz(B, S, C, conf, iou, shift, target, oracle_lib):
     assert np.array_equal(fused.dets[0, :n].cpu().numpy().view(np.uint32), ref.dets.view(np.uint32))
 
 
+@pytest.mark.parametrize("radius,n_gt", [(1, 12), (3, 20)])
+def test_fused_cluttered(radius, n_gt, oracle_lib):
+    """Detector-like clutter (every GT lights up a neighbourhood of heavily overlapping candidates): several extraction
+    batches per image, NMS chains across batches and -- with the production floor target -- floors that run dry.
+    Same bit-exact contract as everywhere else."""
+    B, S, C = 4, 640, 10
+    heads = syn.make_head(B, S, C, seed=77)
+    targets = syn.make_targets(B, S, C, seed=77, n_min=n_gt, n_max=n_gt)
+    syn.light_up_neighbourhoods(heads, targets, radius=radius)
+    dh = _to_dev(heads)
+    shape, info = FeatureShape(S, S), default_anchor_info()
+    det = N.get_detections(shape, dh, info)
+    two_step = N.nms_padded(det, 0.001, 0.6)
+    fused = N.eval_tail(shape, dh, info, 0.001, 0.6)
+    assert torch.equal(fused.counts, two_step.counts)
+    assert torch.equal(fused.dets, two_step.dets) and torch.equal(fused.keep_idx, two_step.keep_idx)
+    _check_nms_against(fused, on.non_max_suppression(det.cpu().numpy(), 0.001, 0.6))
+
+
 def _match_oracle(dets_list, targets, C):
     o = om.CocoMapOracle(C)
     ms = []

@@ -17,6 +17,8 @@ dev = torch.device("cuda:0")
 heads = syn.make_head(B, S, C, seed=2023, device=dev)
 targets = syn.make_targets(B, S, C, seed=2023)
 syn.inject_ground_truth(heads, targets, S, 0.3)
+if len(sys.argv) > 1:  # detector-like clutter: trace_nms.py <radius>
+    syn.light_up_neighbourhoods(heads, targets, radius=int(sys.argv[1]))
 net = [DetectionHeadResult(*lv) for lv in heads]
 gt_count = torch.zeros(C, dtype=torch.long, device=dev)
 lib = L.lib()
