@@ -469,11 +469,16 @@ __global__ void __launch_bounds__(CW_WARPS * 32, 6) cand_floor_kernel(const __gr
     {
         const int nld = in_range ? min(C, CGROUP) : 0;
         const float* cp = cls_base + cell0;
+        if (nld == NQ) {  // the usual case: every class slot of the group is real -- no per-copy predicate
 #pragma unroll
-        for (int u = 0; u < NQ; ++u) {
-            if (u < nld) cp_async16_s_ef(sq0 + u * (WT_CELLS * 4), cp, l2pol);
-            else *reinterpret_cast<float4*>(&sm.q[u][cell0]) = zero4;
-            cp += cls_step;
+            for (int u = 0; u < NQ; ++u) cp_async16_s_ef(sq0 + u * (WT_CELLS * 4), cp + (int64_t)u * cls_step, l2pol);
+        } else {
+#pragma unroll
+            for (int u = 0; u < NQ; ++u) {
+                if (u < nld) cp_async16_s_ef(sq0 + u * (WT_CELLS * 4), cp, l2pol);
+                else *reinterpret_cast<float4*>(&sm.q[u][cell0]) = zero4;
+                cp += cls_step;
+            }
         }
     }
     cp_async_commit();
@@ -677,16 +682,13 @@ __global__ void __launch_bounds__(CW_WARPS * 32, 6) cand_floor_kernel(const __gr
                     if (cm[v] & (1u << u)) *lp++ = (unsigned short)(idb | u);
             }
         } else {
-            // the few pairs that reach the floor
+            // the few pairs that reach the floor: ONE loop over the lane's four cell masks (most lanes have none)
             int slot = warp_excl_scan_i(hot, lane);
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                unsigned m = hm[v];
-                while (m) {
-                    const int u = __ffs(m) - 1;
-                    m &= m - 1;
-                    sm.list[slot++] = (unsigned short)(((cell0 + v) << 4) | u);
-                }
+            unsigned long long hb = (unsigned long long)(hm[0] | (hm[1] << 16)) | ((unsigned long long)(hm[2] | (hm[3] << 16)) << 32);
+            while (hb) {
+                const int bi = __ffsll((long long)hb) - 1;
+                hb &= hb - 1;
+                sm.list[slot++] = (unsigned short)(((cell0 + (bi >> 4)) << 4) | (bi & 15));
             }
         }
         __syncwarp();  // list, q stash and o are visible to the whole warp
