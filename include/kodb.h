@@ -144,6 +144,14 @@ int kodb_train_tail(const kodb_head_level* heads_h /* [3] */, const kodb_level_c
                     float* losses /* dev [3] */, int32_t* n_assigned /* dev [3] or NULL */,
                     void* workspace, int64_t workspace_bytes, void* stream);
 
+/* kodb_iou_aligned: IoUCalculator.__call__(boxes1, boxes2) (kod/core/bbox/iou.py:249-268 -> compute_iou :77-95,
+ * compute_giou :136-161, compute_diou :164-197, compute_ciou :200-246) on two aligned (n, 4) xyxy fp32 arrays.
+ * out (n,) receives the metric (may be NULL when only gradients are wanted).  If grad1 / grad2 are non-NULL they
+ * receive upstream[i] * d(metric_i)/d(boxes1_i) / d(boxes2_i) as (n, 4) (upstream NULL = ones): the gradient autograd
+ * derives from the reference's op chain (CIoU's alpha is a constant, iou.py:241-242).  16-byte aligned pointers. */
+int kodb_iou_aligned(const float* boxes1, const float* boxes2, int64_t n, int32_t iou_type, float eps, float* out,
+                     const float* upstream, float* grad1, float* grad2, void* stream);
+
 /* ---- eval tail ---------------------------------------------------------------------------------
  * kodb_decode: DefaultYolov5Experiment.get_detections (exp.py:70-102): (B, AC, 5+C) contiguous fp32,
  * rows ll|ml|hl, r = (a*H+y)*W+x, columns x1,y1,x2,y2,sigmoid(obj),sigmoid(cls).  Inputs untouched. */
@@ -169,6 +177,9 @@ typedef struct kodb_nms_out {
     int64_t* keep_idx;  /* (B, max_det): index into the candidate list handed to torchvision.ops.nms */
     int32_t* counts;    /* (B,) */
     int32_t* num_candidates; /* (B,) candidates before the max_nms cut (diagnostic) */
+    int64_t* keep_key;  /* (B, max_det) or NULL: row * num_classes + class of every kept detection, i.e. WHICH
+                           (anchor-cell, class) pair of the (B, AC, 5+C) matrix it is (nms.py:46-48); -1 padding.
+                           Unlike keep_idx it does not shift when an unrelated candidate flips at the conf edge. */
 } kodb_nms_out;
 
 /* Ground truth + outputs of the per-class IoU matching (pycoco_map_eval.py:50-106 -> COCOeval.evaluateImg).

@@ -75,7 +75,7 @@ class NmsCfg(C.Structure):
 class NmsOut(C.Structure):
     _fields_ = [
         ("dets", C.c_void_p), ("keep_idx", C.c_void_p), ("counts", C.c_void_p),
-        ("num_candidates", C.c_void_p),
+        ("num_candidates", C.c_void_p), ("keep_key", C.c_void_p),
     ]
 
 
@@ -97,6 +97,7 @@ SIGNATURES = {
     "kodb_train_tail": (C.c_int, [C.POINTER(HeadLevel), C.POINTER(LevelCfg), C.POINTER(Targets),
                                   C.POINTER(LossCfg), _P, C.POINTER(C.c_float), _P, C.c_int32,
                                   C.POINTER(GradLevel), _P, _P, _P, C.c_int64, _P]),
+    "kodb_iou_aligned": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_float, _P, _P, _P, _P, _P]),
     "kodb_decode": (C.c_int, [C.POINTER(HeadLevel), C.POINTER(LevelCfg), C.c_int32, C.c_int32, _P, _P]),
     "kodb_eval_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int64, C.c_int32]),
     "kodb_nms": (C.c_int, [_P, C.c_int32, C.c_int64, C.POINTER(NmsCfg), C.POINTER(NmsOut),

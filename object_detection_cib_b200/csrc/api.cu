@@ -1,7 +1,7 @@
 // Version / error-string entry points of libkodb.
 #include "kodb_common.cuh"
 
-extern "C" int kodb_version(void) { return 100; }
+extern "C" int kodb_version(void) { return 200; }
 
 extern "C" const char* kodb_error_string(int code) {
     switch (code) {

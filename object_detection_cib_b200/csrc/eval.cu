@@ -1726,10 +1726,11 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) select_nms_kernel(const __grid
     float4 rb = make_float4(0.f, 0.f, 0.f, 0.f);
     float rs = 0.0f;
     int rc = -1;
-    long long ridx = 0;
+    long long ridx = 0, rkey = -1;
     if (tid < nk) {
         const unsigned long long ck = s.kept_ck[tid];
         const uint32_t k32 = (uint32_t)ck;
+        rkey = (long long)k32;
         const int row = (int)(k32 / (uint32_t)C);
         rc = (int)(k32 - (uint32_t)row * (uint32_t)C);
         rs = score_of_key((uint32_t)(ck >> 32));
@@ -1741,6 +1742,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) select_nms_kernel(const __grid
         const bool v = tid < nk;
         d[0] = rb.x; d[1] = rb.y; d[2] = rb.z; d[3] = rb.w; d[4] = rs; d[5] = v ? (float)rc : 0.0f;
         p.out.keep_idx[(int64_t)b * max_det + tid] = v ? ridx : -1;
+        if (p.out.keep_key) p.out.keep_key[(int64_t)b * max_det + tid] = rkey;
     }
     if (tid == 0) {
         p.out.counts[b] = nk;

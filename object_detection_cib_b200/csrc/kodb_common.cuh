@@ -51,7 +51,6 @@ __device__ __forceinline__ float exp_fast(float x) {  // |x| <= 87 (callers clam
     const float e = ex2_approx(y);
     return fmaf(e, r * 0.693147182464599609375f, e);
 }
-// eval-side sigmoid (decode + candidate filter share it, so the fused path and get_detections agree bit for bit)
 __device__ __forceinline__ float rcp_approx(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -62,10 +61,12 @@ __device__ __forceinline__ float lg2_approx(float x) {
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-__device__ __forceinline__ float sigmoid_eval(float x) {
-    const float t = fminf(fmaxf(-x, -87.0f), 87.0f);
-    return rcp_approx(1.0f + exp_fast(t));
-}
+// Eval-side sigmoid: decode, the candidate filter's exact tests, the listed scores and the box decode all use THIS
+// function, and it is torch's CUDA sigmoid bit for bit -- ATen's sigmoid_kernel_cuda computes
+// 1.0f / (1.0f + std::exp(-x)) in fp32 with libdevice's expf and an IEEE division -- so heads -> keep indices match the
+// reference executed on the GPU exactly (layers.py:57-89).  The streaming pre-tests of the candidate kernel (logit
+// windows) stay approximate; every decision inside a window is re-taken with this function.
+__device__ __forceinline__ float sigmoid_eval(float x) { return 1.0f / (1.0f + expf(-x)); }
 // softplus(x) and sigmoid(x) for the dense objectness pass
 __device__ __forceinline__ float softplus_sigmoid_fast(float x, float* sig) {
     const float e = exp_fast(-fminf(fabsf(x), 87.0f));  // (0, 1]

@@ -30,6 +30,7 @@ class NmsResult(NamedTuple):
     keep_idx: torch.Tensor  # (B, max_det) int64 index into the candidate list handed to NMS; -1 padding
     counts: torch.Tensor  # (B,) int32
     num_candidates: torch.Tensor  # (B,) int32 candidates before the max_nms cut
+    keep_key: torch.Tensor = None  # (B, max_det) int64 row * C + class of every kept detection; -1 padding
 
 
 class MatchRecords(NamedTuple):
@@ -73,10 +74,12 @@ def _alloc_out(B: int, max_det: int, device):
     keep = torch.empty((B, max_det), dtype=torch.long, device=device)
     counts = torch.empty((B,), dtype=torch.int32, device=device)
     ncand = torch.empty((B,), dtype=torch.int32, device=device)
+    key = torch.empty((B, max_det), dtype=torch.long, device=device)
     out = L.NmsOut()
     out.dets, out.keep_idx, out.counts, out.num_candidates = (dets.data_ptr(), keep.data_ptr(), counts.data_ptr(),
                                                               ncand.data_ptr())
-    return NmsResult(dets, keep, counts, ncand), out
+    out.keep_key = key.data_ptr()
+    return NmsResult(dets, keep, counts, ncand, key), out
 
 
 class MatchState(NamedTuple):

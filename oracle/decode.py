@@ -20,9 +20,11 @@ def decode_level(box: torch.Tensor, obj: torch.Tensor, cls: torch.Tensor, stride
                  anchors_px: Sequence[Sequence[float]]):
     B, A, H, W, _ = box.shape
     ys, xs = torch.meshgrid(torch.arange(H).float(), torch.arange(W).float(), indexing="ij")
-    grid = torch.stack((xs, ys), 2).view(1, 1, H, W, 2)
+    # the reference builds grid and anchors on the CPU and moves them to the head's device (layers.py:57-60); run
+    # with CUDA head tensors this executes torch's CUDA elementwise kernels, i.e. what the reference does on a GPU
+    grid = torch.stack((xs, ys), 2).view(1, 1, H, W, 2).to(box.device)
     # torch.tensor(list of int pairs) is int64 in the reference; the product promotes to fp32
-    anc = torch.tensor([[a[0], a[1]] for a in anchors_px]).reshape(1, A, 1, 1, 2)
+    anc = torch.tensor([[a[0], a[1]] for a in anchors_px]).reshape(1, A, 1, 1, 2).to(box.device)
     xy = box[..., 0:2].sigmoid() * 2 + grid - 0.5
     xy = xy * stride
     wh = ((box[..., 2:4].sigmoid() * 2) ** 2) * anc

@@ -3,8 +3,9 @@ stubs of `_ref_harness.py`) on small seeded inputs.  Run in the build container 
 
     python tests/golden/make_golden.py
 
-Writes tests/golden/{assign,loss,decode,nms}_*.npz.  Each file stores the inputs and the reference's
+Writes tests/golden/{assign,loss,decode,nms,evaltail}_*.npz.  Each file stores the inputs and the reference's
 outputs, so the GPU box (which has no /root/reference) can check both the oracle and the CUDA path.
+(`evaltail_*` fixtures store the generator arguments + a checksum of the head logits instead of the logits.)
 No fixture exists for the mAP stage: its arithmetic lives in pycocotools, which is absent
 ("parity unpinned", see oracle/coco_map.py).
 """
@@ -284,9 +285,99 @@ def nms_cases():
     run_nms("nms_over_max", big, 0.001, 0.6)
 
 
+# ------------------------------------------------------------------------------------------------
+# eval tail end to end: heads -> reference get_detections -> reference non_max_suppression
+# ------------------------------------------------------------------------------------------------
+def head_checksum(heads):
+    """A few numbers that pin the regenerated logits to the ones the fixture was made from."""
+    parts = [t.double().sum().item() for lv in heads for t in lv]
+    parts += [float(lv[2].reshape(-1)[::9973][:8].double().sum()) for lv in heads]
+    return np.array(parts, np.float64)
+
+
+def run_evaltail(name, B, S, C, seed, obj_shift=0.0, inject=0.3, clutter=0, n_gt=None, conf=0.001, iou=0.6):
+    """Heads are regenerated by the test from (B, S, C, seed, ...) with synthetic.make_head (same torch build in
+    the build container and on the GPU box) and checked against `head_sums`."""
+    heads = syn.make_head(B, S, C, seed=seed, obj_shift=obj_shift)
+    targets = syn.make_targets(B, S, C, seed=seed, n_min=n_gt or 0, n_max=n_gt or 10)
+    if clutter:
+        syn.light_up_neighbourhoods(heads, targets, radius=clutter)
+    elif inject > 0:
+        syn.inject_ground_truth(heads, targets, S, fraction=inject, seed=seed)
+    sums = head_checksum(heads)
+    det = _Exp().get_detections(FeatureShape(width=S, height=S), net_result(heads))  # (clones: heads stay intact)
+    rec = []
+    real = torchvision.ops.nms
+
+    def spy(boxes, scores, thr):
+        keep = real(boxes, scores, thr)
+        rec.append((boxes.clone(), scores.clone(), keep.clone()))
+        return keep
+
+    torchvision.ops.nms = spy
+    try:
+        res = ref_nms_mod.non_max_suppression(det.clone(), conf_thres=conf, nms_thres=iou)
+    finally:
+        torchvision.ops.nms = real
+    out = {"meta": np.array([B, S, C, seed, clutter, n_gt or -1], np.int64),
+           "fmeta": np.array([obj_shift, inject, conf, iou], np.float64), "head_sums": sums,
+           "counts": np.array([r.shape[0] for r in res], np.int64)}
+    keeps, keys, rows, ncand = [], [], [], []
+    call = 0
+    for b, r in enumerate(res):
+        rows.append(r.numpy().reshape(-1, 6))
+        if not r.shape[0]:
+            ncand.append(0)
+            continue
+        boxes, scores, keep = rec[call]
+        call += 1
+        # identity (row, class) of every candidate handed to NMS: nms.py:33-63 re-run with torch ops
+        x = det[b]
+        xc = x[:, 4] > conf
+        rid = xc.nonzero().squeeze(1)
+        x = x[xc].clone()
+        x[:, 5:] *= x[:, 4:5]
+        if C > 1:
+            i, j = (x[:, 5:] > conf).nonzero(as_tuple=False).T
+            cs = x[i, j + 5]
+        else:
+            cs, j = x[:, 5:].max(1)
+            m = cs > conf
+            i, j, cs = m.nonzero().squeeze(1), j[m], cs[m]
+        key = rid[i] * C + j
+        n0 = int(key.shape[0])
+        if n0 > 30000:
+            order = cs.argsort(descending=True)[:30000]
+            key, cs = key[order], cs[order]
+        assert torch.equal(cs, scores), "candidate replay differs from what the reference handed to NMS"
+        k = keep[:300]
+        assert torch.equal(r[:, 4], cs[k])
+        keeps.append(k.numpy())
+        keys.append(key[k].numpy())
+        ncand.append(n0)
+    assert call == len(rec)
+    out["keep_idx"] = np.concatenate(keeps) if keeps else np.zeros((0,), np.int64)
+    out["keep_key"] = np.concatenate(keys) if keys else np.zeros((0,), np.int64)
+    out["rows"] = np.concatenate(rows, 0).astype(np.float32)
+    out["ncand"] = np.array(ncand, np.int64)
+    save(name, **out)
+
+
+def evaltail_cases():
+    run_evaltail("evaltail_cfg1", 8, 640, 10, seed=2024)                 # BASELINE config[0]: B=8, 640, C=10
+    run_evaltail("evaltail_cfg3", 24, 640, 10, seed=2026, inject=0.5)    # cfg 2/3 shape (per-image work is batch-independent)
+    run_evaltail("evaltail_cfg5", 2, 1280, 80, seed=2028)                # cfg 5: > 30000 candidates, the top-k cut
+    run_evaltail("evaltail_s416", 4, 416, 10, seed=2029, obj_shift=2.0)  # the reference's default input: 13x13 grid
+    run_evaltail("evaltail_clutter", 2, 640, 10, seed=2030, clutter=2, n_gt=12)  # detector-like clutter
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "evaltail":
+        evaltail_cases()
+        sys.exit(0)
     assign_cases()
     loss_cases()
     decode_cases()
     nms_cases()
+    evaltail_cases()

@@ -66,6 +66,32 @@ def test_nms_matches_reference(name, oracle_lib):
             assert r.candidates.shape[0] == int(g[f"ncand_{b}"][0])
 
 
+@pytest.mark.parametrize("name", G.names("evaltail_"))
+def test_evaltail_matches_reference(name, oracle_lib):
+    """heads -> oracle decode -> oracle NMS against the real reference run end to end (get_detections ->
+    non_max_suppression on the CPU): counts, keep indices, candidate identities and rows, bit for bit.  A bounded
+    number of images per fixture keeps the CPU suite short (the O(n^2) scan costs 1-2 s per dense image)."""
+    g = G.load(name)
+    heads, _, (B, S, C), (conf, iou) = G.evaltail_inputs(g)
+    check = list(range(B))[:2] + ([B - 1] if B > 2 else [])
+    # decode the WHOLE batch like the reference did: torch's CPU sigmoid is vectorised with a scalar tail, so the last
+    # bit of a value depends on where the element sits in the tensor; a sliced batch would not reproduce it
+    det = od.get_detections(heads, LEVELS).numpy()[check]
+    res = on.non_max_suppression(det, conf, iou)
+    ref = G.evaltail_split(g)
+    for r, b in zip(res, check):
+        kidx, kkey, rows = ref[b]
+        assert r.dets.shape[0] == int(g["counts"][b]), (name, b)
+        assert np.array_equal(r.keep, kidx), (name, b)
+        got_rows, got_key = r.dets, r.cand_row[r.keep] * C + r.dets[:, 5].astype(np.int64)
+        if r.n_before_cut > on.MAX_NMS:  # unstable argsort in the reference: exact ties in implementation-defined order
+            got_rows, got_key = G.canon_ties(got_rows, got_key)
+            rows, kkey = G.canon_ties(rows, kkey)
+        assert np.array_equal(got_rows.view(np.uint32), rows.view(np.uint32)), (name, b)
+        assert np.array_equal(got_key, kkey), (name, b)
+        assert r.n_before_cut == int(g["ncand"][b])
+
+
 def test_greedy_nms_against_torchvision(oracle_lib):
     """The C restatement against the third-party kernel it restates (torchvision.ops.nms, CPU)."""
     tv = pytest.importorskip("torchvision")
