@@ -207,6 +207,25 @@ def pack_targets(targets: Sequence, device) -> PackedTargets:
     return PackedTargets(s, (boxes, labels, offsets), T, B, s.max_per_image, counts)
 
 
+def check_labels_host(targets, num_classes: int) -> None:
+    """Reference behaviour for a class id outside [0, C): `target_labels_one_hot[range(n), labels] = 1`
+    (loss.py:145-152) raises IndexError.  Checked here whenever the labels are still on the host (tuple of CPU
+    tensors, or a collated blob that has not been moved yet) -- a handful of integers, no device sync.  Labels that
+    arrive on the device are checked by the train-tail kernel instead (NaN classification loss + error flag)."""
+    from .data import HostPackedTargets
+
+    if isinstance(targets, PackedTargets):
+        return
+    if isinstance(targets, HostPackedTargets):
+        labs = [targets.labels] if not targets.labels.is_cuda else []
+    else:
+        labs = [t[1].reshape(-1) for t in targets if not t[1].is_cuda and t[1].numel()]
+    for l in labs:
+        if l.numel() and (int(l.min()) < 0 or int(l.max()) >= num_classes):
+            bad = int(l.max()) if int(l.max()) >= num_classes else int(l.min())
+            raise IndexError(f"target label {bad} is out of range for {num_classes} classes")
+
+
 # ---- workspaces -----------------------------------------------------------------------------------
 _WORKSPACES: dict = {}
 _MAX_CACHED = 8

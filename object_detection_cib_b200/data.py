@@ -29,8 +29,12 @@ def _round16(n: int) -> int:
 
 
 class HostPackedTargets(Sequence):
-    """Flat host copy of the targets of one batch: `boxes (T,4)`, `labels (T,) int64`, `offsets (B+1,) int32`,
-    all views of ONE uint8 blob `[boxes | labels | offsets]` with 16-byte aligned sections."""
+    """Flat copy of the targets of one batch: `boxes (T,4)`, `labels (T,) int64`, `offsets (B+1,) int32`,
+    all views of ONE uint8 blob `[boxes | labels | offsets]` with 16-byte aligned sections.
+
+    Built on the host by the collate function; `.to(device)` moves the blob with one copy and returns the same
+    kind of object, so Lightning's `transfer_batch_to_device` (which calls `.to` on anything that has it instead of
+    rebuilding the sequence element by element) carries it to the GPU intact."""
 
     def __init__(self, blob: torch.Tensor, counts: Sequence[int], f64: bool):
         self.blob = blob
@@ -75,9 +79,24 @@ class HostPackedTargets(Sequence):
 
     def pin_memory(self) -> "HostPackedTargets":
         """DataLoader(pin_memory=True) protocol for custom batch types."""
-        if self.blob.is_pinned():
+        if self.blob.is_cuda or self.blob.is_pinned():
             return self
         return HostPackedTargets(self.blob.pin_memory(), self.counts, self.f64)
+
+    def to(self, device=None, *args, non_blocking: bool = True, **kwargs) -> "HostPackedTargets":
+        """Move the blob (ONE copy) and keep the packed form.  Having `.to` makes the object a transferable leaf for
+        `lightning.pytorch.utilities.move_data_to_device` / `apply_to_collection`, which would otherwise try to
+        rebuild this Sequence as `type(self)([...])`.  dtype arguments are ignored (boxes keep their precision)."""
+        if device is None or isinstance(device, torch.dtype):
+            return self
+        device = torch.device(device)
+        if device == self.blob.device:
+            return self
+        return HostPackedTargets(self.blob.to(device, non_blocking=non_blocking), self.counts, self.f64)
+
+    @property
+    def device(self) -> torch.device:
+        return self.blob.device
 
     # ---- Sequence[DetectionTarget] ----------------------------------------------------------------------
     def __len__(self) -> int:
@@ -90,7 +109,8 @@ class HostPackedTargets(Sequence):
             i += len(self)
         if not 0 <= i < len(self):
             raise IndexError(i)
-        lo, hi = int(self.offsets[i]), int(self.offsets[i + 1])
+        lo = sum(self.counts[:i])  # host-side lengths: no device sync when the blob lives on the GPU
+        hi = lo + self.counts[i]
         return DetectionTarget(self.boxes[lo:hi], self.labels[lo:hi])
 
     @property

@@ -108,6 +108,7 @@ class Yolov5Loss(nn.Module):
         ratios = (hp.lambda_ll_objectness, hp.lambda_ml_objectness, hp.lambda_hl_objectness)
         levels = H.level_cfgs(self.assigner.anchor_info, image_feature_shape.width, image_feature_shape.height, ratios)
         H.check_grid(heads, levels)
+        H.check_labels_host(targets, heads.num_classes)
         packed = targets if isinstance(targets, H.PackedTargets) else H.pack_targets(targets, dev)
         if packed.batch != heads.batch:
             raise ValueError(f"{packed.batch} target entries for a batch of {heads.batch}")

@@ -41,9 +41,15 @@ def _xyxy(c: torch.Tensor) -> tuple[torch.Tensor, ...]:
 
 
 def aligned_iou(pred_cxcywh: torch.Tensor, gt_cxcywh: torch.Tensor, iou_type: str = "ciou", eps: float = 1e-7):
-    """iou.py:77-246.  Index 1 = prediction, g = ground truth."""
-    x1, y1, x2, y2 = _xyxy(pred_cxcywh)
-    x1g, y1g, x2g, y2g = _xyxy(gt_cxcywh)
+    """iou.py:77-246 on cxcywh boxes (loss.py:84-93 converts before calling the calculator)."""
+    return aligned_iou_xyxy(torch.stack(_xyxy(pred_cxcywh), -1), torch.stack(_xyxy(gt_cxcywh), -1), iou_type, eps)
+
+
+def aligned_iou_xyxy(boxes1: torch.Tensor, boxes2: torch.Tensor, iou_type: str = "ciou", eps: float = 1e-7):
+    """IoUCalculator.__call__ (iou.py:249-268) -> compute_{iou,giou,diou,ciou} (iou.py:77-246) on (..., 4) xyxy
+    boxes.  Index 1 = boxes1 (prediction), g = boxes2 (ground truth).  Pinned by tests/golden/iou_*.npz."""
+    x1, y1, x2, y2 = boxes1.unbind(-1)
+    x1g, y1g, x2g, y2g = boxes2.unbind(-1)
     iw = (torch.min(x2, x2g) - torch.max(x1, x1g)).clamp(0)
     ih = (torch.min(y2, y2g) - torch.max(y1, y1g)).clamp(0)
     inter = iw * ih

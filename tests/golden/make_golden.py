@@ -371,8 +371,35 @@ def evaltail_cases():
     run_evaltail("evaltail_clutter", 2, 640, 10, seed=2030, clutter=2, n_gt=12)  # detector-like clutter
 
 
+# ------------------------------------------------------------------------------------------------
+# standalone IoUCalculator (iou.py:249-268), forward + autograd to both inputs
+# ------------------------------------------------------------------------------------------------
+def iou_cases():
+    g = torch.Generator().manual_seed(61)
+    n = 192
+    c1 = torch.rand(n, 2, generator=g) * 100
+    s1 = 4 + torch.rand(n, 2, generator=g) * 60
+    # 2/3 of the pairs overlap (jittered copies), 1/3 are unrelated boxes (mostly disjoint)
+    c2 = torch.where(torch.arange(n)[:, None] % 3 < 2, c1 + torch.randn(n, 2, generator=g) * 8,
+                     torch.rand(n, 2, generator=g) * 100)
+    s2 = s1 * (0.5 + torch.rand(n, 2, generator=g))
+    b1 = torch.cat((c1 - s1 / 2, c1 + s1 / 2), 1).float()
+    b2 = torch.cat((c2 - s2 / 2, c2 + s2 / 2), 1).float()
+    up = torch.randn(n, generator=g).float()
+    for it in ("iou", "giou", "diou", "ciou"):
+        a = b1.clone().requires_grad_(True)
+        b = b2.clone().requires_grad_(True)
+        out = IoUCalculator(IoUType(it), eps=1e-7)(a, b)
+        (out * up).sum().backward()
+        save(f"iou_{it}", boxes1=b1.numpy(), boxes2=b2.numpy(), upstream=up.numpy(), out=out.detach().numpy(),
+             grad1=a.grad.numpy(), grad2=b.grad.numpy(), iou_type=np.array([it]))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "iou":
+        iou_cases()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "evaltail":
         evaltail_cases()
         sys.exit(0)
@@ -381,3 +408,4 @@ if __name__ == "__main__":
     decode_cases()
     nms_cases()
     evaltail_cases()
+    iou_cases()

@@ -369,6 +369,28 @@ def test_matching_and_ap(B, S, C, dtype, oracle_lib):
     assert abs(got2["avg_mAP"] - want["avg_mAP"]) < 1e-4
 
 
+def test_coco_rule_kats_gpu():
+    """The hand-derived pycocotools known answers (tests/_coco_kats.py) through the CUDA matching + AP kernels, fed
+    the way the reference's callback feeds its evaluator (python lists, pycoco_map_eval.py:66-106)."""
+    import _coco_kats as K
+    for case in K.CASES:
+        C, ious = case["num_classes"], case["ious"]
+        ev = DeviceCocoMapEvaluator(C, ious=ious, device=DEV)
+        preds = [[(float(r[5]), float(r[4]), float(r[0]), float(r[1]), float(r[2]), float(r[3])) for r in dets]
+                 for dets, _, _ in case["images"]]
+        gts = [[(int(l), *[float(v) for v in bx]) for bx, l in zip(gb, gl)] for _, gb, gl in case["images"]]
+        ev.add_predictions(preds, gts)
+        tp = ev._records[0].tp.cpu().numpy()
+        for (img, d), want in case["tp"].items():
+            assert [bool((tp[img, d] >> t) & 1) for t in range(4)] == want, (case["name"], img, d)
+        ap = ev.average_precision().cpu().numpy()
+        for (t, k), want in case["ap"].items():
+            if want is None:
+                assert np.isnan(ap[t, k]), (case["name"], t, k)
+            else:
+                assert abs(ap[t, k] - want) < 1e-12, (case["name"], t, k, ap[t, k], want)
+
+
 def test_ap_accumulate_many_images(oracle_lib):
     """Accumulation over several batches with score ties across images (stable order matters)."""
     C, B = 5, 40

@@ -109,3 +109,68 @@ def test_packed_targets_work_with_a_dataloader():
     assert len(batches) == 2
     _, t, _ = batches[1]
     assert isinstance(t, HostPackedTargets) and t.counts == [0, 1, 2] and float(t[2].boxes[0, 0]) == 5.0
+
+
+# ---- Lightning's batch transfer: apply_to_collection must not rebuild the packed targets ---------------
+def _apply_to_collection(data, dtype, function, *args, **kwargs):
+    """lightning_utilities.core.apply_func.apply_to_collection, restated for the container types a detection batch
+    holds (lightning is not installed here): a leaf of `dtype` goes through `function`; mappings, namedtuples and
+    generic Sequences are REBUILT as `type(data)(...)` from their transformed elements."""
+    from collections.abc import Mapping, Sequence
+    if isinstance(data, dtype):
+        return function(data, *args, **kwargs)
+    elem_type = type(data)
+    if isinstance(data, Mapping):
+        return elem_type({k: _apply_to_collection(v, dtype, function, *args, **kwargs) for k, v in data.items()})
+    is_nt = isinstance(data, tuple) and hasattr(data, "_fields")
+    if is_nt or (isinstance(data, Sequence) and not isinstance(data, str)):
+        out = [_apply_to_collection(d, dtype, function, *args, **kwargs) for d in data]
+        return elem_type(*out) if is_nt else elem_type(out)
+    return data
+
+
+def test_packed_targets_survive_lightning_batch_transfer():
+    from abc import ABC
+    from object_detection_cib_b200.data import HostPackedTargets, packed_collate_fn
+    from object_detection_cib_b200.types import DetectionTarget
+
+    class Transferable(ABC):
+        @classmethod
+        def __subclasshook__(cls, subclass):
+            return callable(getattr(subclass, "to", None)) if cls is Transferable else NotImplemented
+
+    dev = torch.device("cpu")
+    moved = []
+
+    def batch_to(data):  # lightning.fabric.utilities.apply_func.move_data_to_device::batch_to
+        kwargs = {"non_blocking": True} if isinstance(data, torch.Tensor) else {}
+        out = data.to(dev, **kwargs)
+        moved.append(type(data).__name__)
+        return out
+
+    targets = [DetectionTarget(torch.rand(n, 4), torch.randint(0, 10, (n,))) for n in (2, 0, 3)]
+    batch = packed_collate_fn([(torch.zeros(3, 4, 4), t, ("p", (4, 4))) for t in targets])
+    out = _apply_to_collection(batch, Transferable, batch_to)
+    imgs, packed, info = out
+    assert isinstance(packed, HostPackedTargets) and packed.counts == [2, 0, 3]  # a leaf: moved with ONE .to()
+    assert moved.count("HostPackedTargets") == 1 and info == batch[2]
+    for got, want in zip(packed, targets):
+        assert torch.equal(got.boxes, want.boxes) and torch.equal(got.labels, want.labels)
+    # .to() keeps the packed form on another device type too (meta: no data, just the plumbing)
+    m = packed.to("meta")
+    assert isinstance(m, HostPackedTargets) and m.device.type == "meta" and m[2].boxes.shape == (3, 4)
+    assert packed.to(torch.float32) is packed and packed.to("cpu") is packed
+    # without `.to` the rebuild path would have raised: HostPackedTargets([...]) has no such constructor
+    with pytest.raises(TypeError):
+        HostPackedTargets([t for t in packed])
+
+
+def test_out_of_range_labels_raise_like_the_reference():
+    """loss.py:145-152 indexes a one-hot matrix with the labels: an id outside [0, C) is an IndexError there."""
+    from object_detection_cib_b200 import _host as H
+    t = [(torch.tensor([[1.0, 2, 30, 40]]), torch.tensor([10])), (torch.zeros(0, 4), torch.zeros(0, dtype=torch.long))]
+    with pytest.raises(IndexError, match="label"):
+        H.check_labels_host(t, 10)
+    with pytest.raises(IndexError, match="label"):
+        H.check_labels_host([(torch.tensor([[1.0, 2, 30, 40]]), torch.tensor([-1]))], 10)
+    H.check_labels_host([(torch.tensor([[1.0, 2, 30, 40]]), torch.tensor([9]))], 10)

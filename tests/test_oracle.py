@@ -45,6 +45,19 @@ def test_loss_matches_reference(name):
             np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=1e-5, atol=1e-9)
 
 
+@pytest.mark.parametrize("name", G.names("iou_"))
+def test_iou_calculator_matches_reference(name):
+    """oracle.loss.aligned_iou_xyxy against the real IoUCalculator (forward bit-exact, autograd to both inputs)."""
+    g = G.load(name)
+    a = torch.from_numpy(g["boxes1"]).requires_grad_(True)
+    b = torch.from_numpy(g["boxes2"]).requires_grad_(True)
+    out = ol.aligned_iou_xyxy(a, b, str(g["iou_type"][0]), 1e-7)
+    assert np.array_equal(out.detach().numpy().view(np.uint32), g["out"].view(np.uint32))
+    (out * torch.from_numpy(g["upstream"])).sum().backward()
+    np.testing.assert_allclose(a.grad.numpy(), g["grad1"], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(b.grad.numpy(), g["grad2"], rtol=1e-6, atol=1e-9)
+
+
 @pytest.mark.parametrize("name", G.names("decode_"))
 def test_decode_matches_reference(name):
     g = G.load(name)
@@ -142,6 +155,32 @@ def test_coco_map_known_answers(oracle_lib):
     m = om.match_image(d, gtb, np.array([0, 0]), 1)
     ap = om.average_precision(m.score, m.cls, m.tp, m.gt_count)
     assert abs(ap[1, 0] - (51 + 50 * (2 / 3)) / 101) < 1e-12
+
+
+def test_coco_rule_kats():
+    """Every pycocotools rule the restatement relies on, against answers derived by hand (tests/_coco_kats.py)."""
+    import _coco_kats as K
+    for case in K.CASES:
+        C, ious = case["num_classes"], case["ious"]
+        orc = om.CocoMapOracle(C, ious)
+        ms = []
+        for dets, gtb, gtl in case["images"]:
+            m = om.match_image(dets, gtb, gtl, C, ious)
+            ms.append(m)
+            orc._matches.append(m)
+        for (img, d), want in case["tp"].items():
+            assert ms[img].tp[d].tolist() == want, (case["name"], img, d)
+        s = np.concatenate([m.score for m in ms]); c = np.concatenate([m.cls for m in ms])
+        tp = np.concatenate([m.tp for m in ms], 0); gcount = np.sum([m.gt_count for m in ms], 0)
+        ap = om.average_precision(s, c, tp, gcount)
+        for (t, k), want in case["ap"].items():
+            if want is None:
+                assert np.isnan(ap[t, k]), (case["name"], t, k)
+            else:
+                assert abs(ap[t, k] - want) < 1e-12, (case["name"], t, k, ap[t, k], want)
+        rep = orc.get_report()
+        if 0.5 in ious:
+            assert sorted(rep["tag_wise_AP_50"]) == sorted(k for (t, k), w in case["ap"].items() if t == 1 and w is not None)
 
 
 def test_bbiou_c_matches_numpy(oracle_lib):

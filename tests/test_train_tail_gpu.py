@@ -160,3 +160,47 @@ def test_collated_targets_equal_the_tuple_form():
     for ga, gb in zip(out[0][1], out[1][1]):
         assert torch.equal(ga, gb)
     assert torch.equal(out[0][2], out[1][2]) and torch.equal(out[0][3], out[1][3])
+
+
+# ---- standalone IoUCalculator (iou.py:249-268) ------------------------------------------------------------------------
+@pytest.mark.parametrize("name", G.names("iou_"))
+def test_iou_calculator_golden(name):
+    """IoUCalculator.__call__ on the CUDA kernel against the real reference: values to fp32 rounding (atan, division),
+    gradients to both inputs at rtol 1e-5."""
+    from object_detection_cib_b200.iou import IoUCalculator, IoUType
+    g = G.load(name)
+    a = torch.from_numpy(g["boxes1"]).to(DEV).requires_grad_(True)
+    b = torch.from_numpy(g["boxes2"]).to(DEV).requires_grad_(True)
+    out = IoUCalculator(IoUType(str(g["iou_type"][0])), 1e-7)(a, b)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), g["out"], rtol=2e-6, atol=2e-7)
+    (out * torch.from_numpy(g["upstream"]).to(DEV)).sum().backward()
+    for got, want in ((a.grad, g["grad1"]), (b.grad, g["grad2"])):
+        np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-5, atol=1e-5 * np.abs(want).max())
+
+
+@pytest.mark.parametrize("it", ["iou", "giou", "diou", "ciou"])
+def test_iou_calculator_vs_oracle_batched(it):
+    """(B, N, 4) inputs, one input without grad, forward-only call."""
+    from object_detection_cib_b200.iou import IoUCalculator, IoUType
+    gen = torch.Generator().manual_seed(17)
+    c = torch.rand(3, 4097, 2, generator=gen) * 300
+    s = 2 + torch.rand(3, 4097, 2, generator=gen) * 90
+    b1 = torch.cat((c - s / 2, c + s / 2), -1)
+    c2 = c + torch.randn(3, 4097, 2, generator=gen) * 15
+    s2 = s * (0.6 + 0.8 * torch.rand(3, 4097, 2, generator=gen))
+    b2 = torch.cat((c2 - s2 / 2, c2 + s2 / 2), -1)
+    want_in = b1.clone().requires_grad_(True)
+    want = ol.aligned_iou_xyxy(want_in, b2, it, 1e-7)
+    want.sum().backward()
+    calc = IoUCalculator(IoUType(it))
+    a = b1.to(DEV).requires_grad_(True)
+    got = calc(a, b2.to(DEV))
+    assert got.shape == (3, 4097)
+    np.testing.assert_allclose(got.detach().cpu().numpy(), want.detach().numpy(), rtol=2e-6, atol=2e-7)
+    got.sum().backward()
+    wg = want_in.grad.numpy()
+    np.testing.assert_allclose(a.grad.cpu().numpy(), wg, rtol=1e-5, atol=1e-5 * np.abs(wg).max())
+    with torch.no_grad():
+        assert torch.equal(calc(b1.to(DEV), b2.to(DEV)), got.detach())
+    with pytest.raises(RuntimeError):
+        calc(b1, b2)  # CPU tensors: no fallback
