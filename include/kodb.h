@@ -9,8 +9,9 @@
  * Conventions
  *  - All pointers are DEVICE pointers unless the parameter name ends in `_h` (host).
  *  - The caller owns every buffer (inputs, outputs, workspaces); the library never allocates or frees
- *    device memory and keeps no global state.  Workspaces must be zero-filled once after allocation;
- *    kernels leave them in a reusable state.
+ *    device memory and keeps no global state.  Workspaces must be zero-filled once after allocation
+ *    (by the caller or with kodb_workspace_reset); kernels leave them in a reusable state.  After a failed
+ *    launch (KODB_ERR_LAUNCH, a CUDA error on the stream) call kodb_workspace_reset before reusing one.
  *  - Work is enqueued on `stream` (a cudaStream_t passed as void*); no call synchronises the host.
  *  - Return value: 0 = OK, negative = error (KODB_ERR_*); nothing throws across the ABI.
  *    `kodb_error_string(code)` gives a static description.
@@ -90,7 +91,8 @@ typedef struct kodb_targets {
     int32_t num_targets;        /* T */
     int32_t batch;              /* B */
     int32_t max_per_image;      /* max_b (img_offsets[b+1]-img_offsets[b]), known on the host; the matching stage
-                                   takes at most 512 boxes per image (KODB_ERR_CAPACITY beyond) */
+                                   keeps up to 512 boxes per image in shared memory and reads them from global
+                                   memory beyond that (slower, same results) */
 } kodb_targets;
 
 /* Yolov5LossParams (loss.py:25-43) + IoUCalculator(iou_type, eps) (iou.py:249-268). */
@@ -134,8 +136,20 @@ int kodb_assign(const kodb_level_cfg* levels_h, const kodb_targets* targets_h, f
  * kernel exits without touching anything (used by autograd backward when the forward already
  * produced the gradients for the hinted upstream, e.g. training_step's batch_size factor,
  * exp.py:124-130).  n_assigned (device int32[3], may be NULL) receives N_l.
- * workspace: kodb_train_workspace_bytes() bytes, zero-initialised once. */
-int64_t kodb_train_workspace_bytes(int32_t batch, int32_t max_targets_per_image);
+ * workspace: kodb_train_workspace_bytes(batch, max boxes per image, max anchors per cell over the levels, C) bytes,
+ * zero-initialised once.  There is no limit on the number of boxes per image: the per-(image, level) row records
+ * live in shared memory while they fit (~58 boxes per image with 3 anchors) and in the workspace beyond that
+ * (slower, same results).
+ * A target label outside [0, C) (IndexError in the reference, loss.py:145-152) turns the three losses into NaN and
+ * raises bit 0 of the status word (kodb_train_status); the host wrappers reject such labels before the launch when the
+ * labels are still on the host. */
+int64_t kodb_train_workspace_bytes(int32_t batch, int32_t max_targets_per_image, int32_t max_anchors_per_cell,
+                                   int32_t num_classes);
+/* Status bits of the most recent kodb_train_tail launch that used `workspace` (synchronises `stream`):
+ * bit 0 = label out of range, bit 1 = a bounded in-kernel wait expired (results of that launch are invalid). */
+int kodb_train_status(const void* workspace, int32_t* status_h, void* stream);
+/* Asynchronous zero-fill of any kodb workspace on `stream`: first use, or recovery after a failed launch. */
+int kodb_workspace_reset(void* workspace, int64_t workspace_bytes, void* stream);
 int kodb_train_tail(const kodb_head_level* heads_h /* [3] */, const kodb_level_cfg* levels_h /* [3] */,
                     const kodb_targets* targets_h, const kodb_loss_cfg* cfg_h,
                     const float* pos_weight /* dev [C] or NULL: Yolov5Loss.weights, loss.py:58-63 */,
@@ -151,6 +165,16 @@ int kodb_train_tail(const kodb_head_level* heads_h /* [3] */, const kodb_level_c
  * derives from the reference's op chain (CIoU's alpha is a constant, iou.py:241-242).  16-byte aligned pointers. */
 int kodb_iou_aligned(const float* boxes1, const float* boxes2, int64_t n, int32_t iou_type, float eps, float* out,
                      const float* upstream, float* grad1, float* grad2, void* stream);
+
+/* kodb_sgd_step: one optimizer step of torch.optim.SGD(momentum, nesterov) over SmartOptimizer's parameter groups
+ * (kod/nn/optim/smart.py:11-60) with the per-group lr / momentum of the warm-up updater
+ * (kod/lightning/experiments/yv5_baseline/warmup.py:11-58).  params / grads / momentum are flat fp32 arenas holding
+ * the groups back to back; seg_begin_h (host, num_groups + 1 float offsets, multiples of 4) delimits them; hyper is a
+ * DEVICE array [num_groups][4] = (lr, momentum, weight_decay, dampening), so the launch never synchronises and can
+ * be captured into a CUDA graph.  momentum must be zero before the first step (== torch's buf = clone(d_p)).
+ * zero_grads != 0 also writes grads = 0 (replaces optimizer.zero_grad()). */
+int kodb_sgd_step(float* params, float* grads, float* momentum, const int64_t* seg_begin_h, int32_t num_groups,
+                  const float* hyper, int32_t nesterov, int32_t zero_grads, void* stream);
 
 /* ---- eval tail ---------------------------------------------------------------------------------
  * kodb_decode: DefaultYolov5Experiment.get_detections (exp.py:70-102): (B, AC, 5+C) contiguous fp32,

@@ -93,11 +93,14 @@ SIGNATURES = {
     "kodb_error_string": (C.c_char_p, [C.c_int]),
     "kodb_assign": (C.c_int, [C.POINTER(LevelCfg), C.POINTER(Targets), C.c_float, C.POINTER(AssignOut),
                               C.c_int32, _P, _P]),
-    "kodb_train_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "kodb_train_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "kodb_train_status": (C.c_int, [_P, C.POINTER(C.c_int32), _P]),
+    "kodb_workspace_reset": (C.c_int, [_P, C.c_int64, _P]),
     "kodb_train_tail": (C.c_int, [C.POINTER(HeadLevel), C.POINTER(LevelCfg), C.POINTER(Targets),
                                   C.POINTER(LossCfg), _P, C.POINTER(C.c_float), _P, C.c_int32,
                                   C.POINTER(GradLevel), _P, _P, _P, C.c_int64, _P]),
     "kodb_iou_aligned": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_float, _P, _P, _P, _P, _P]),
+    "kodb_sgd_step": (C.c_int, [_P, _P, _P, C.POINTER(C.c_int64), C.c_int32, _P, C.c_int32, C.c_int32, _P]),
     "kodb_decode": (C.c_int, [C.POINTER(HeadLevel), C.POINTER(LevelCfg), C.c_int32, C.c_int32, _P, _P]),
     "kodb_eval_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int64, C.c_int32]),
     "kodb_nms": (C.c_int, [_P, C.c_int32, C.c_int64, C.POINTER(NmsCfg), C.POINTER(NmsOut),

@@ -129,7 +129,8 @@ class Yolov5Loss(nn.Module):
             if self.weights.numel() != heads.num_classes:
                 raise ValueError("len(weights) must equal the number of classes")
             pw = self.weights
-        nbytes = L.lib().kodb_train_workspace_bytes(packed.batch, packed.max_per_image)
+        nbytes = L.lib().kodb_train_workspace_bytes(packed.batch, packed.max_per_image,
+                                                    max(lv.num_anchors for lv in levels), heads.num_classes)
         return TrainTailPlan(heads, levels, packed, cfg, pw, H.workspace("train", dev, nbytes))
 
     def forward(self, image_feature_shape: FeatureShape, net_result, targets) -> LossResult:

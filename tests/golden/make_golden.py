@@ -395,8 +395,62 @@ def iou_cases():
              grad1=a.grad.numpy(), grad2=b.grad.numpy(), iou_type=np.array([it]))
 
 
+# ------------------------------------------------------------------------------------------------
+# optimizer step + warm-up: SmartOptimizer(SGD nesterov) + OptimizerWarmupUpdater + sch_linear
+# ------------------------------------------------------------------------------------------------
+def _small_net(seed):
+    import torch.nn as nn
+    torch.manual_seed(seed)
+    return nn.Sequential(nn.Conv2d(3, 8, 3, bias=False), nn.BatchNorm2d(8), nn.SiLU(), nn.Conv2d(8, 5, 1, bias=True),
+                         nn.GroupNorm(1, 5), nn.Flatten(), nn.LazyLinear(7))
+
+
+def sgd_cases():
+    from functools import partial
+    from kod.nn.optim.smart import SmartOptimizer
+    from kod.nn.optim.schedulers import sch_linear
+    from kod.lightning.experiments.yv5_baseline.warmup import OptimizerWarmupUpdater
+    net = _small_net(71)
+    net(torch.zeros(1, 3, 6, 6))  # materialise the lazy layer
+    names = [n for n, _ in net.named_parameters()]
+    params = dict(net.named_parameters())
+    opt = SmartOptimizer(partial(torch.optim.SGD, lr=0.01, momentum=0.937, nesterov=True), weight_decay=0.0005)(net)
+    for pg in opt.param_groups:
+        pg.setdefault("initial_lr", pg["lr"])  # what LambdaLR.__init__ records (schedulers.py:41-45)
+    upd = OptimizerWarmupUpdater(warmup_epochs=3, warmup_bias_lr=0.1, warmup_momentum=0.8, momentum=0.937)
+    sch = partial(sch_linear, max_epochs=30, lrf=0.01)
+    out = {"names": np.array(names), "group_names": np.array([pg["name"] for pg in opt.param_groups])}
+    group_of = {}
+    for gi, pg in enumerate(opt.param_groups):
+        for q in pg["params"]:
+            group_of[id(q)] = gi
+    out["group_index"] = np.array([group_of[id(params[n])] for n in names], np.int64)
+    for n in names:
+        out[f"init/{n}"] = params[n].detach().numpy().copy()
+    g = torch.Generator().manual_seed(72)
+    steps, nw = 7, 5  # warm-up for steps 0..5 (exp.py:166-185: global_step > nw returns early), plain SGD afterwards
+    hyper = []
+    for step in range(steps):
+        for n in names:
+            gr = torch.randn(params[n].shape, generator=g) * 0.1
+            params[n].grad = gr.clone()
+            out[f"grad{step}/{n}"] = gr.numpy()
+        if step <= nw:
+            upd(current_step=step, current_epoch=step // 3, max_warmup_steps=nw, sch_fn=sch, optimizer=opt)
+        hyper.append([[float(pg["lr"]), float(pg["momentum"]), float(pg["weight_decay"])] for pg in opt.param_groups])
+        opt.step()
+    out["hyper"] = np.array(hyper, np.float64)
+    for n in names:
+        out[f"final/{n}"] = params[n].detach().numpy().copy()
+        out[f"mom/{n}"] = opt.state[params[n]]["momentum_buffer"].numpy().copy()
+    save("sgd_warmup", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "sgd":
+        sgd_cases()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "iou":
         iou_cases()
         sys.exit(0)
@@ -409,3 +463,4 @@ if __name__ == "__main__":
     nms_cases()
     evaltail_cases()
     iou_cases()
+    sgd_cases()

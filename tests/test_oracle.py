@@ -183,6 +183,35 @@ def test_coco_rule_kats():
             assert sorted(rep["tag_wise_AP_50"]) == sorted(k for (t, k), w in case["ap"].items() if t == 1 and w is not None)
 
 
+def test_sgd_warmup_matches_reference():
+    """oracle.sgd against SmartOptimizer(SGD nesterov) + OptimizerWarmupUpdater run by the real reference classes:
+    the interpolated lr / momentum per group and step, and parameters / momentum buffers after 7 steps, bit for bit."""
+    from functools import partial
+    from oracle import sgd as osgd
+    g = G.load("sgd_warmup")
+    names = [str(n) for n in g["names"]]
+    gname = [str(n) for n in g["group_names"]]
+    assert gname == ["bias_params", "decay_params", "norm_params"]  # smart.py:42-58
+    gi = g["group_index"]
+    assert [gname[i] for i in gi] == ["decay_params", "norm_params", "bias_params", "decay_params", "bias_params",
+                                      "norm_params", "bias_params", "decay_params", "bias_params"]
+    sch = partial(osgd.sch_linear, max_epochs=30, lrf=0.01)
+    P = {n: g[f"init/{n}"] for n in names}
+    M = {n: None for n in names}
+    steps, nw = g["hyper"].shape[0], 5
+    hyper = [[0.01, 0.937, wd] for wd in (0.0, 0.0005, 0.0)]
+    for step in range(steps):
+        if step <= nw:
+            for k in range(3):
+                hyper[k][0], hyper[k][1] = osgd.warmup_hyper(step, step // 3, nw, gname[k], 0.01, 0.1, 0.8, 0.937, sch)
+        assert np.array_equal(np.array(hyper), g["hyper"][step]), step
+        for n, k in zip(names, gi):
+            P[n], M[n] = osgd.sgd_step(P[n], g[f"grad{step}/{n}"], M[n], *hyper[k])
+    for n in names:
+        assert np.array_equal(P[n].view(np.uint32), g[f"final/{n}"].view(np.uint32)), n
+        assert np.array_equal(M[n].view(np.uint32), g[f"mom/{n}"].view(np.uint32)), n
+
+
 def test_bbiou_c_matches_numpy(oracle_lib):
     rng = np.random.default_rng(3)
     d = rng.uniform(0, 50, (17, 4)); g = rng.uniform(0, 50, (9, 4))

@@ -43,14 +43,18 @@ lib.kodb_debug_set_train_trace(None)
 t = trace.cpu().numpy().reshape(NG, 8).astype(np.float64)
 used = t[:, 0] > 0
 t0 = t[used, 0].min()
-nd = int(used.sum()) - B * 3
+nd = int(used.sum()) - B * 3  # dense CTAs come first in block order
 d = t[:nd]
 sp = t[nd:nd + B * 3]
-print("dense CTAs", nd, "start min/max us", (d[:, 0].min() - t0) / 1e3, (d[:, 0].max() - t0) / 1e3, "end min/max", (d[:, 1].min() - t0) / 1e3,
-      (d[:, 1].max() - t0) / 1e3)
-names = ["start", "N_l", "rows", "waited", "patched", "partials", "final"]
-for k in range(6):
-    v = (sp[:, k] - t0) / 1e3
-    print(f"sparse {names[k]:9s} min={v.min():7.1f} mean={v.mean():7.1f} max={v.max():7.1f} us")
-fin = sp[:, 6].max()
-print("finaliser end us", (fin - t0) / 1e3, "losses", losses.tolist())
+us = lambda a: (a - t0) / 1e3
+print(f"dense CTAs {nd}: start {us(d[:, 0]).min():.1f}..{us(d[:, 0]).max():.1f}  end {us(d[:, 1]).min():.1f}..{us(d[:, 1]).max():.1f} us")
+print(f"sparse CTAs {B * 3}: start {us(sp[:, 0]).min():.1f}..{us(sp[:, 0]).max():.1f}")
+for nm, k in (("GT+scan", 1), ("gathers+iou", 4), ("dup scan", 5), ("cls", 2), ("published", 3), ("dense seen", 6), ("patched", 7)):
+    v = us(sp[:, k])
+    v = v[v > -1e6]
+    print(f"  sparse {nm:12s} min {v.min():6.1f} mean {v.mean():6.1f} p90 {np.percentile(v, 90):6.1f} max {v.max():6.1f}")
+fin = sp[sp[:, 2] > sp[:, 3]]
+if len(fin):
+    print(f"finalising sparse CTA: published {us(fin[:, 3]).max():.1f}, losses out at {us(fin[:, 2]).max():.1f} us")
+print("tail after the last dense CTA ended: %.1f us" % (us(sp[:, 7]).max() - us(d[:, 1]).max()))
+print("losses", losses.tolist(), "N_l", nass.tolist())
