@@ -115,7 +115,8 @@ SIGNATURES = {
                                      C.c_int64, _P]),
 }
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libkodb.so")
+# (KODB_LIB: another build of the same C ABI, for A/B timing of kernel versions on one box)
+LIB_PATH = os.environ.get("KODB_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libkodb.so")
 _lib = None
 
 

@@ -85,8 +85,9 @@ class DeviceCocoMapEvaluator(object):
         self.add_detection_list(dets, tg)
 
     # ---- report -----------------------------------------------------------------------------------
-    def average_precision(self) -> torch.Tensor:
-        """(len(ious), C) fp64 AP table on the device (NaN where a class has no ground truth)."""
+    def average_precision(self, gather: bool = True) -> torch.Tensor:
+        """(len(ious), C) fp64 AP table on the device (NaN where a class has no ground truth).  Under torch.distributed
+        the records of all ranks are gathered first (global AP on every rank); `gather=False` keeps it local."""
         dev = self.device
         if self._records:
             score = torch.cat([r.score for r in self._records], 0)
@@ -98,7 +99,9 @@ class DeviceCocoMapEvaluator(object):
             cls = torch.zeros((0, self.max_det), dtype=torch.int32, device=dev)
             tp = torch.zeros((0, self.max_det), dtype=torch.uint8, device=dev)
             counts = torch.zeros((0,), dtype=torch.int32, device=dev)
-        score, cls, tp, counts, gt_count = D.gather_records(score, cls, tp, counts, self.gt_count)
+        gt_count = self.gt_count
+        if gather:
+            score, cls, tp, counts, gt_count = D.gather_records(score, cls, tp, counts, gt_count)
         lib = L.lib()
         n_img = int(counts.shape[0])
         ap = torch.empty((L.NUM_IOU_THRS, self.num_classes), dtype=torch.float64, device=dev)
@@ -108,9 +111,9 @@ class DeviceCocoMapEvaluator(object):
                                        ws.data_ptr(), ws.numel(), H.stream_ptr(dev)), "kodb_ap_accumulate")
         return ap
 
-    def get_report(self) -> dict:
+    def get_report(self, gather: bool = True) -> dict:
         """Keys consumed at pycoco_map_eval.py:113-125."""
-        ap = self.average_precision().cpu()  # the one D2H copy of the epoch
+        ap = self.average_precision(gather).cpu()  # the one D2H copy of the epoch
         rep: dict = {}
         per_t = []
         for ti, t in enumerate(self.ious):

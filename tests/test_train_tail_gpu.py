@@ -115,6 +115,55 @@ def test_loss_vs_oracle(B, S, C, upstream):
     _assert_grads_close(grads, want_g)
 
 
+@pytest.mark.parametrize("B,S,C,n_gt", [(2, 640, 10, 150), (3, 320, 80, 70)])
+def test_loss_crowded_images(B, S, C, n_gt):
+    """No limit on boxes per image (the reference has none): beyond ~58 boxes the per-(image, level) row records spill
+    from shared memory to the workspace (and with 80 classes the class gradients are recomputed instead of stored).
+    Same losses / gradients as the oracle; many boxes share cells, so the duplicate chains get long."""
+    heads = syn.make_head(B, S, C, seed=S + n_gt)
+    targets = syn.make_targets(B, S, C, seed=n_gt, n_min=n_gt, n_max=n_gt, size_lo=8, size_hi=120)
+    hp = Yolov5LossParams.get_default()
+    losses, grads, mod = _run_cuda_loss(heads, targets, S, hp, "ciou", None)
+    asg = oa.assign([(b.numpy(), l.numpy()) for b, l in targets], LEVELS, S, S)
+    assert mod.last_num_assigned.tolist() == [a.samples.shape[0] for a in asg]
+    want_l, want_g = ol.loss_forward_backward(heads, asg, S, ol.LossHParams(*hp), "ciou", 1e-7, None, upstream=(B, B, B))
+    np.testing.assert_allclose(losses, np.array([float(v) for v in want_l], np.float32), rtol=1e-5)
+    _assert_grads_close(grads, want_g)
+
+
+def test_out_of_range_label_on_the_device_gives_nan_and_a_status_bit():
+    """loss.py:145-152 raises IndexError for a class id outside [0, C).  Labels that are already on the device cannot be
+    checked without a sync, so the kernel turns the losses of that launch into NaN and raises a status bit; the next
+    launch with valid labels is clean again (the workspace re-arms itself)."""
+    import ctypes
+    from object_detection_cib_b200 import _lib as L
+    B, S, C = 2, 128, 4
+    heads = [DetectionHeadResult(*[t.to(DEV) for t in lv]) for lv in syn.make_head(B, S, C, seed=3)]
+    good = _tt(syn.make_targets(B, S, C, seed=4, n_min=2, n_max=4, size_hi=100), DEV)
+    bad = [(b.clone(), l.clone()) for b, l in good]
+    bad[1][1][0] = C  # one label out of range
+    mod = _loss_module(Yolov5LossParams.get_default(), "ciou", None)
+    with torch.no_grad():
+        r = mod(FeatureShape(S, S), heads, bad)
+        plan = mod.plan(FeatureShape(S, S), heads, bad)
+        assert all(bool(torch.isnan(v)) for v in r)
+        st = ctypes.c_int32(-1)
+        L.check(L.lib().kodb_train_status(plan.workspace.data_ptr(), ctypes.byref(st), None), "kodb_train_status")
+        assert st.value & 1
+        r2 = mod(FeatureShape(S, S), heads, good)
+        assert not any(bool(torch.isnan(v)) for v in r2)
+        L.check(L.lib().kodb_train_status(plan.workspace.data_ptr(), ctypes.byref(st), None), "kodb_train_status")
+        assert st.value == 0
+        # kodb_workspace_reset re-arms a workspace explicitly (recovery path after a failed launch)
+        plan.workspace.fill_(0xAB)
+        L.check(L.lib().kodb_workspace_reset(plan.workspace.data_ptr(), plan.workspace.numel(), None), "kodb_workspace_reset")
+        r3 = mod(FeatureShape(S, S), heads, good)
+        assert all(torch.equal(a, b) for a, b in zip(r2, r3))
+    # host-side labels are rejected before the launch, like the reference
+    with pytest.raises(IndexError):
+        mod(FeatureShape(S, S), heads, [(b.cpu(), l.cpu()) for b, l in bad])
+
+
 def test_loss_no_grad_and_determinism():
     B, S, C = 4, 256, 10
     heads = [DetectionHeadResult(*[t.to(DEV) for t in lv]) for lv in syn.make_head(B, S, C, seed=1)]
