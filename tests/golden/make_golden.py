@@ -446,8 +446,72 @@ def sgd_cases():
     save("sgd_warmup", **out)
 
 
+# ------------------------------------------------------------------------------------------------
+# box transforms of the augmentation pipeline: mosaic, random perspective, flip, mixup
+# ------------------------------------------------------------------------------------------------
+def augment_cases():
+    import random
+    from kod.data.mosaic import MosaicAugmentor
+    from kod.data.types import AugmentedSample
+    from kod.data.augmentations import default as AD
+    rng = np.random.default_rng(81)
+    out = {}
+    S = 320
+    for case in range(4):
+        tiles = []
+        for i in range(4):
+            h, w = int(rng.integers(120, 400)), int(rng.integers(120, 400))
+            n = int(rng.integers(1, 9))
+            c = rng.uniform(0, 1, (n, 2)) * [w, h]
+            wh = rng.uniform(6, 160, (n, 2))
+            b = np.concatenate((c - wh / 2, c + wh / 2), 1)
+            b[:, [0, 2]] = b[:, [0, 2]].clip(0, w - 1)
+            b[:, [1, 3]] = b[:, [1, 3]].clip(0, h - 1)
+            tiles.append(AugmentedSample(image=np.zeros((h, w, 3), np.uint8), bboxes=b, labels=rng.integers(0, 10, n)))
+        random.seed(900 + case)
+        res, border = MosaicAugmentor(S)(tiles)
+        random.seed(900 + case)  # replay the centre draw (mosaic.py:51-54)
+        yc, xc = (int(random.uniform(-x, 2 * S + x)) for x in border)
+        for i, t in enumerate(tiles):
+            out[f"mosaic{case}/tile{i}_boxes"] = t.bboxes
+            out[f"mosaic{case}/tile{i}_labels"] = t.labels
+            out[f"mosaic{case}/tile{i}_wh"] = np.array([t.image.shape[1], t.image.shape[0]], np.int64)
+        out[f"mosaic{case}/center"] = np.array([xc, yc], np.int64)
+        out[f"mosaic{case}/out_boxes"] = res.bboxes
+        out[f"mosaic{case}/out_labels"] = res.labels
+        # the mosaic result goes through random_perspective with the mosaic border (default.py:279-351)
+        vals = AD.AffineRandValues(perspective_x=0.0 if case % 2 == 0 else 2e-4, perspective_y=0.0 if case % 2 == 0 else -1e-4,
+                                   degrees=float(rng.uniform(-10, 10)), scale=float(rng.uniform(0.6, 1.4)),
+                                   shear_x=float(rng.uniform(-3, 3)), shear_y=float(rng.uniform(-3, 3)),
+                                   translate_x=float(rng.uniform(0.4, 0.6)), translate_y=float(rng.uniform(0.4, 0.6)))
+        persp = AD.random_perspective(res, vals, border=border)
+        im = res.image
+        feat = AD._get_feat_shape(width=im.shape[1], height=im.shape[0], border=border)
+        M = AD._get_combined_matrix(affine_values=vals, feat_shape=FeatureShape(width=im.shape[1], height=im.shape[0]),
+                                    feat_shape_with_border=feat, round_off=False)
+        out[f"affine{case}/M"] = M
+        out[f"affine{case}/out_wh"] = np.array([feat.width, feat.height], np.int64)
+        out[f"affine{case}/perspective_scale"] = np.array([float(vals.perspective_x != 0 or vals.perspective_y != 0), vals.scale])
+        out[f"affine{case}/out_boxes"] = persp.bboxes
+        out[f"affine{case}/out_labels"] = persp.labels
+        flipped = AD.horizontal_flip(AugmentedSample(np.zeros((feat.height, feat.width, 3), np.uint8), persp.bboxes, persp.labels))
+        out[f"flip{case}/out_boxes"] = flipped.bboxes
+        if case:
+            prev = AugmentedSample(np.zeros((feat.height, feat.width, 3), np.float64), out[f"flip{case - 1}/out_boxes"],
+                                   out[f"affine{case - 1}/out_labels"])
+            cur = AugmentedSample(np.zeros((feat.height, feat.width, 3), np.float64), flipped.bboxes, flipped.labels)
+            np.random.seed(3)
+            mx = AD.mixup(prev, cur)
+            out[f"mixup{case}/out_boxes"] = mx.bboxes
+            out[f"mixup{case}/out_labels"] = mx.labels
+    save("augment_boxes", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "augment":
+        augment_cases()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "sgd":
         sgd_cases()
         sys.exit(0)
@@ -464,3 +528,4 @@ if __name__ == "__main__":
     evaltail_cases()
     iou_cases()
     sgd_cases()
+    augment_cases()

@@ -174,3 +174,39 @@ def test_out_of_range_labels_raise_like_the_reference():
     with pytest.raises(IndexError, match="label"):
         H.check_labels_host([(torch.tensor([[1.0, 2, 30, 40]]), torch.tensor([-1]))], 10)
     H.check_labels_host([(torch.tensor([[1.0, 2, 30, 40]]), torch.tensor([9]))], 10)
+
+
+# ---- box transforms of the augmentation pipeline against the real reference ---------------------------
+def test_augment_box_transforms_match_the_reference():
+    """mosaic (mosaic.py:133-158), random perspective (default.py:250-276, :336-345), horizontal flip (:385-397) and mixup
+    (:400-408): boxes and labels bit for bit against the reference functions (tests/golden/augment_boxes.npz), and the
+    result collates into the packed blob."""
+    import _golden as G
+    from object_detection_cib_b200 import data as D
+    from object_detection_cib_b200.types import DetectionTarget
+    g = G.load("augment_boxes")
+    collated = []
+    for case in range(4):
+        tiles = [(g[f"mosaic{case}/tile{i}_boxes"], g[f"mosaic{case}/tile{i}_labels"]) for i in range(4)]
+        shapes = [tuple(int(v) for v in g[f"mosaic{case}/tile{i}_wh"]) for i in range(4)]
+        xc, yc = (int(v) for v in g[f"mosaic{case}/center"])
+        mb, ml = D.mosaic_targets(tiles, shapes, (xc, yc), 320)
+        assert np.array_equal(mb, g[f"mosaic{case}/out_boxes"]) and np.array_equal(ml, g[f"mosaic{case}/out_labels"])
+        persp, scale = g[f"affine{case}/perspective_scale"]
+        ab, al = D.affine_targets(mb, ml, g[f"affine{case}/M"], tuple(int(v) for v in g[f"affine{case}/out_wh"]),
+                                  bool(persp), float(scale))
+        assert np.array_equal(ab, g[f"affine{case}/out_boxes"]) and np.array_equal(al, g[f"affine{case}/out_labels"])
+        fb = D.flip_targets(ab, int(g[f"affine{case}/out_wh"][0]))
+        assert np.array_equal(fb, g[f"flip{case}/out_boxes"])
+        if case:
+            xb, xl = D.mixup_targets((g[f"flip{case - 1}/out_boxes"], g[f"affine{case - 1}/out_labels"]), (fb, al))
+            assert np.array_equal(xb, g[f"mixup{case}/out_boxes"]) and np.array_equal(xl, g[f"mixup{case}/out_labels"])
+            fb, al = xb, xl
+        collated.append((torch.zeros(3, 4, 4), DetectionTarget(torch.from_numpy(fb), torch.from_numpy(al.astype(np.int64))), None))
+    _, packed, _ = D.packed_collate_fn(collated)
+    assert packed.f64 and packed.num_targets == sum(int(c[1].labels.shape[0]) for c in collated)
+    # a tile without boxes contributes nothing; the placement windows tile the canvas around the centre
+    b, l = D.mosaic_targets([(np.zeros((0, 4)), np.zeros((0,)))] * 4, [(100, 100)] * 4, (320, 320), 320)
+    assert b.shape == (0, 4) and l.shape == (0,)
+    (x1a, y1a, x2a, y2a), (x1b, y1b, x2b, y2b), (padw, padh) = D.mosaic_placement(0, 300, 280, 200, 150, 320)
+    assert (x2a - x1a, y2a - y1a) == (x2b - x1b, y2b - y1b) and (padw, padh) == (x1a - x1b, y1a - y1b)
