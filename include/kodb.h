@@ -166,6 +166,29 @@ int kodb_train_tail(const kodb_head_level* heads_h /* [3] */, const kodb_level_c
 int kodb_iou_aligned(const float* boxes1, const float* boxes2, int64_t n, int32_t iou_type, float eps, float* out,
                      const float* upstream, float* grad1, float* grad2, void* stream);
 
+/* One pyramid level of the Detect head (kod/nn/heads/yolov5.py:134-178): the feature map and the parameters of its
+ * three 1x1 convolutions, and the three planar output tensors. */
+typedef struct kodb_head_conv_level {
+    const float* x;       /* (B, in_channels, H, W) contiguous fp32 */
+    const float* weight;  /* (A*(5+C), in_channels): box rows, objectness rows, class rows -- the three conv weights
+                             back to back (yolov5.py:21-26, :104-109, :55-60) */
+    const float* bias_box; /* (A*4,) */
+    const float* bias_obj; /* (A,)   */
+    const float* bias_cls; /* (A*C,) */
+    float* out_box;       /* (B, A*4, H, W): viewed (B,A,H,W,4) by Rearrange("b (a p) h w -> b a h w p") */
+    float* out_obj;       /* (B, A,   H, W) */
+    float* out_cls;       /* (B, A*C, H, W) */
+    int32_t in_channels, H, W;
+} kodb_head_conv_level;
+
+/* kodb_head_forward: Yolov5Head.forward (kod/nn/heads/yolov5.py:170-178) of up to three pyramid levels in one launch:
+ * per level the box / objectness / class 1x1 convolutions as ONE tf32 tensor-core GEMM that reads the feature map once
+ * and writes the three planar tensors.  fp32 in, tf32 multiply, fp32 accumulate + bias (the precision class of torch's
+ * default convolution policy, torch.backends.cudnn.allow_tf32).  in_channels % 32 == 0, H*W % 4 == 0,
+ * A*(5+C) <= 256; KODB_ERR_UNSUPPORTED otherwise (callers fall back to the three separate convolutions themselves). */
+int kodb_head_forward(const kodb_head_conv_level* levels_h /* [num_levels], 1..3 */, int32_t num_levels, int32_t batch,
+                      int32_t num_anchors, int32_t num_classes, void* stream);
+
 /* kodb_sgd_step: one optimizer step of torch.optim.SGD(momentum, nesterov) over SmartOptimizer's parameter groups
  * (kod/nn/optim/smart.py:11-60) with the per-group lr / momentum of the warm-up updater
  * (kod/lightning/experiments/yv5_baseline/warmup.py:11-58).  params / grads / momentum are flat fp32 arenas holding

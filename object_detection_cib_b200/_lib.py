@@ -64,6 +64,14 @@ class AssignOut(C.Structure):
     ]
 
 
+class HeadConvLevel(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("weight", C.c_void_p), ("bias_box", C.c_void_p), ("bias_obj", C.c_void_p),
+        ("bias_cls", C.c_void_p), ("out_box", C.c_void_p), ("out_obj", C.c_void_p), ("out_cls", C.c_void_p),
+        ("in_channels", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+    ]
+
+
 class NmsCfg(C.Structure):
     _fields_ = [
         ("conf_thres", C.c_float), ("iou_thres", C.c_double), ("max_wh", C.c_float),
@@ -100,6 +108,7 @@ SIGNATURES = {
                                   C.POINTER(LossCfg), _P, C.POINTER(C.c_float), _P, C.c_int32,
                                   C.POINTER(GradLevel), _P, _P, _P, C.c_int64, _P]),
     "kodb_iou_aligned": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_float, _P, _P, _P, _P, _P]),
+    "kodb_head_forward": (C.c_int, [C.POINTER(HeadConvLevel), C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "kodb_sgd_step": (C.c_int, [_P, _P, _P, C.POINTER(C.c_int64), C.c_int32, _P, C.c_int32, C.c_int32, _P]),
     "kodb_decode": (C.c_int, [C.POINTER(HeadLevel), C.POINTER(LevelCfg), C.c_int32, C.c_int32, _P, _P]),
     "kodb_eval_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int64, C.c_int32]),

@@ -1,0 +1,409 @@
+// kodb_head_forward — the Detect head of the reference (kod/nn/heads/yolov5.py:12-178): per pyramid level three 1x1
+// convolutions (box: A*4, objectness: A, class: A*C output channels, with bias) of the same (B, K, H, W) feature map,
+// each followed by Rearrange("b (a p) h w -> b a h w p") -- i.e. three planar [B][A*P][H][W] tensors.
+//
+// Here: ONE persistent tcgen05 kernel for all three levels.  Per level the three convolutions are one GEMM
+//     D[cell][n] = sum_k X[b][k][cell] * W[n][k]          cell = 0..H*W-1 (M), n = 0..A*(5+C)-1 (N), k = 0..K-1
+// with the feature map read ONCE (the reference reads it three times) straight from its NCHW layout:
+//   * A operand = X tile, 128 cells x 32 channels, "MN-major" (cells contiguous): TMA boxes of 32 cells x 32 channels with
+//     the 128-byte swizzle are exactly the canonical UMMA MN-major SW128 atoms (8 channel rows x 128 B), no transposition;
+//   * B operand = the concatenated weights [n][k] (K-major), a 32-channel slab per stage, rows beyond A*(5+C) zero-filled
+//     by the TMA bounds check;
+//   * tf32 MMA (fp32 operands, fp32 accumulation -- the precision class of torch's default conv policy
+//     torch.backends.cudnn.allow_tf32 = True), accumulators in TMEM: 128 lanes (cells) x N columns, double buffered;
+//   * warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread) + TMEM owner, warps 2..5 =
+//     epilogue (tcgen05.ld 32x32b: thread = cell, registers = channels; + bias; stores are 128-byte coalesced along the
+//     cells of ONE output plane, which is precisely the planar layout the detection tail wants).
+// HBM-bound by construction (AI ~ 17 flop/B at K=128, N=45): 4*K bytes in + 4*N bytes out per cell.
+#include <cuda.h>  // CUtensorMap + enums only; the encoder entry point is fetched at run time (no libcuda link dependency)
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <mutex>
+
+#include "kodb_common.cuh"
+
+namespace kodb {
+
+constexpr int HD_TILE_M = 128;   // cells per tile (UMMA M)
+constexpr int HD_KB = 32;        // channels per pipeline stage (one 128-byte swizzle row of fp32)
+constexpr int HD_UMMA_K = 8;     // tf32: 32 bytes of K per instruction
+constexpr int HD_STAGES = 4;
+constexpr int HD_THREADS = 192;  // 6 warps: TMA, MMA, 4 x epilogue
+constexpr int HD_A_STAGE_BYTES = HD_TILE_M * HD_KB * 4;  // 16 KB: four slabs of 32 cells x 32 channels
+
+struct HeadLevelParams {
+    int K, HW, B;
+    int tiles_per_image, tile_begin;
+    int n1, n2, n3;      // channel boundaries: box [0, n1), objectness [n1, n2), class [n2, n3)
+    float* out[3];       // planar [B][channels][HW]
+    const float* bias[3];
+};
+
+struct HeadParams {
+    CUtensorMap tma_x[KODB_NUM_LEVELS];  // (cell, channel, image) fp32, box 32 x 32 x 1, 128B swizzle
+    CUtensorMap tma_w[KODB_NUM_LEVELS];  // (channel, n) fp32, box 32 x n_pad, 128B swizzle
+    HeadLevelParams lv[KODB_NUM_LEVELS];
+    int n_pad;           // UMMA N: A*(5+C) rounded up to 16
+    int acc_cols;        // TMEM columns per accumulator (power of two >= n_pad)
+    int b_stage_bytes;   // n_pad * 128
+    int total_tiles;
+    uint32_t a_layout, a_lbo, a_sbo, a_kadv;  // A-operand descriptor fields
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded: a broken pipeline must not hang the GPU (a trap surfaces as a launch error on the host)
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+        if (spins > (1u << 26)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem desc] * B[smem desc], tf32 inputs, fp32 accumulate, issued by ONE thread for the CTA
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// all MMAs issued so far by this thread have completed -> one arrival on the mbarrier (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, leading / stride byte offsets in
+// 16-byte units, version 1 (sm_100), layout type SWIZZLE_128B
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = 2) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
+    d |= (uint64_t)1 << 46;  // version
+    d |= (uint64_t)layout << 61;  // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
+    return d;
+}
+
+// =========================================================================================================
+__global__ void __launch_bounds__(HD_THREADS, 1) head_forward_kernel(const __grid_constant__ HeadParams p) {
+    extern __shared__ __align__(1024) uint8_t hd_smem_raw[];
+    // 1024-byte alignment of every operand stage (128B swizzle atoms are 1 KB)
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(hd_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + HD_STAGES * HD_A_STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + HD_STAGES * p.b_stage_bytes);
+    uint64_t* full_bar = bars;                    // [HD_STAGES]  TMA -> MMA
+    uint64_t* empty_bar = bars + HD_STAGES;       // [HD_STAGES]  MMA -> TMA
+    uint64_t* tfull_bar = bars + 2 * HD_STAGES;   // [2]          MMA -> epilogue
+    uint64_t* tempty_bar = bars + 2 * HD_STAGES + 2;  // [2]      epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * HD_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int l = 0; l < KODB_NUM_LEVELS; ++l) {
+            tma_prefetch_desc(&p.tma_x[l]);
+            tma_prefetch_desc(&p.tma_w[l]);
+        }
+        for (int s = 0; s < HD_STAGES; ++s) {
+            mbar_init(full_bar + s, 1);
+            mbar_init(empty_bar + s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar + a, 1);
+            mbar_init(tempty_bar + a, 4);  // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // TMEM: two accumulators of acc_cols columns; this warp owns allocation and release
+        const uint32_t ncols = 2u * (uint32_t)p.acc_cols;
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t tx = (uint32_t)(HD_A_STAGE_BYTES + p.b_stage_bytes);
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const int l = t >= p.lv[2].tile_begin ? 2 : (t >= p.lv[1].tile_begin ? 1 : 0);
+                const HeadLevelParams& L = p.lv[l];
+                const int tt = t - L.tile_begin;
+                const int b = tt / L.tiles_per_image, c0 = (tt - b * L.tiles_per_image) * HD_TILE_M;
+                for (int kb = 0; kb < L.K / HD_KB; ++kb) {
+                    mbar_wait(empty_bar + stage, phase ^ 1u);
+                    mbar_expect_tx(full_bar + stage, tx);
+                    uint8_t* a_dst = smem_a + stage * HD_A_STAGE_BYTES;
+#pragma unroll
+                    for (int j = 0; j < HD_TILE_M / 32; ++j)  // slab j: cells c0 + 32j .. + 31 (zero-filled beyond H*W)
+                        tma_load_3d(a_dst + j * (HD_KB * 128), &p.tma_x[l], full_bar + stage, c0 + 32 * j, kb * HD_KB, b);
+                    tma_load_2d(smem_b + stage * p.b_stage_bytes, &p.tma_w[l], full_bar + stage, kb * HD_KB, 0);
+                    if (++stage == HD_STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B tf32, A MN-major, B K-major, N, M = 128
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(p.n_pad >> 3) << 17) |
+                                   ((uint32_t)(HD_TILE_M >> 4) << 24);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const int l = t >= p.lv[2].tile_begin ? 2 : (t >= p.lv[1].tile_begin ? 1 : 0);
+                const int nkb = p.lv[l].K / HD_KB;
+                mbar_wait(tempty_bar + acc, acc_phase ^ 1u);  // the epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_cols);
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(full_bar + stage, phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem_a + stage * HD_A_STAGE_BYTES);
+                    const uint32_t b_addr = smem_u32(smem_b + stage * p.b_stage_bytes);
+#pragma unroll
+                    for (int k = 0; k < HD_KB / HD_UMMA_K; ++k) {
+                        // A (MN-major): slabs of 32 cells are HD_KB*128 bytes apart (LBO), groups of 8 channel rows 1 KB (SBO);
+                        //   one instruction consumes one group -> advance by 1 KB.
+                        // B (K-major): rows of 128 bytes, 8-row groups 1 KB apart (SBO); 8 channels = 32 bytes along the row.
+                        const uint64_t a_desc = umma_smem_desc(a_addr + k * p.a_kadv, p.a_lbo, p.a_sbo, p.a_layout);
+                        const uint64_t b_desc = umma_smem_desc(b_addr + k * 32, 16, 1024);
+                        umma_tf32(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar + stage);  // the stage's operands may be overwritten once these MMAs are done
+                    if (kb == nkb - 1) umma_commit(tfull_bar + acc);  // ... and the accumulator is complete
+                    if (++stage == HD_STAGES) { stage = 0; phase ^= 1u; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> (+ bias) -> planar global stores =====
+        const int q = warp & 3;  // the TMEM lane quadrant this warp may read
+        const int row = 32 * q + lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            const int l = t >= p.lv[2].tile_begin ? 2 : (t >= p.lv[1].tile_begin ? 1 : 0);
+            const HeadLevelParams& L = p.lv[l];
+            const int tt = t - L.tile_begin;
+            const int b = tt / L.tiles_per_image, c0 = (tt - b * L.tiles_per_image) * HD_TILE_M;
+            const int cell = c0 + row;
+            mbar_wait(tfull_bar + acc, acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * p.acc_cols);
+            for (int n0 = 0; n0 < L.n3; n0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(taddr + n0, v);
+                tmem_ld_wait();
+                if (n0 + 16 >= L.n3) {
+                    // last chunk read: hand the accumulator back before the stores go out
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar + acc);
+                }
+                if (cell < L.HW) {
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        const int n = n0 + u;
+                        if (n < L.n3) {
+                            const int ti = n < L.n1 ? 0 : (n < L.n2 ? 1 : 2);
+                            const int nb = ti == 0 ? 0 : (ti == 1 ? L.n1 : L.n2);
+                            const int ch = ti == 0 ? L.n1 : (ti == 1 ? L.n2 - L.n1 : L.n3 - L.n2);
+                            const float bias = __ldg(L.bias[ti] + (n - nb));
+                            // 32 lanes -> 32 consecutive cells of one output plane: a 128-byte store
+                            L.out[ti][((size_t)b * ch + (n - nb)) * L.HW + cell] = __uint_as_float(v[u]) + bias;
+                        }
+                    }
+                }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        const uint32_t ncols = 2u * (uint32_t)p.acc_cols;
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    }
+}
+
+// ---- host -----------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encoder() {
+    static EncodeTiledFn fn = nullptr;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+}  // namespace kodb
+
+extern "C" int kodb_head_forward(const kodb_head_conv_level* levels_h, int32_t num_levels, int32_t batch, int32_t num_anchors,
+                                 int32_t num_classes, void* stream) {
+    using namespace kodb;
+    if (!levels_h || num_levels < 1 || num_levels > KODB_NUM_LEVELS || batch < 1 || num_anchors < 1 || num_anchors > KODB_MAX_ANCHORS || num_classes < 1 ||
+        num_classes > KODB_MAX_CLASSES)
+        return KODB_ERR_INVALID_ARGUMENT;
+    const int n3 = num_anchors * (5 + num_classes);
+    const int n_pad = (n3 + 15) / 16 * 16;
+    if (n_pad > 256) return KODB_ERR_UNSUPPORTED;  // one UMMA tile in N (3 anchors: up to 80 classes)
+    EncodeTiledFn encode = get_encoder();
+    if (!encode) return KODB_ERR_UNSUPPORTED;
+    HeadParams p;
+    p.n_pad = n_pad;
+    p.acc_cols = 32;
+    while (p.acc_cols < n_pad) p.acc_cols *= 2;
+    p.b_stage_bytes = n_pad * 128;
+    // A operand (MN-major tf32): the only legal shared-memory layout is the 128-byte swizzle with a 32-byte atom
+    // (cutlass sm100_common.inl:92) -- atoms of 4 channel rows x 128 B; 8 channels per instruction = 2 atoms (SBO 512 B
+    // apart); 32-cell slabs HD_KB*128 bytes apart (LBO)
+    int x_swizzle = (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    p.a_layout = 1; p.a_lbo = HD_KB * 128; p.a_sbo = 512; p.a_kadv = 1024;
+    if (const char* dbg = getenv("KODB_HD_DBG")) {  // probing aid: "swizzle,layout,lbo,sbo,kadv"
+        int v[5];
+        if (sscanf(dbg, "%d,%d,%d,%d,%d", v, v + 1, v + 2, v + 3, v + 4) == 5) {
+            x_swizzle = v[0]; p.a_layout = v[1]; p.a_lbo = v[2]; p.a_sbo = v[3]; p.a_kadv = v[4];
+        }
+    }
+    int tiles = 0;
+    for (int l = 0; l < num_levels; ++l) {
+        const kodb_head_conv_level& h = levels_h[l];
+        if (!h.x || !h.weight || !h.out_box || !h.out_obj || !h.out_cls || !h.bias_box || !h.bias_obj || !h.bias_cls)
+            return KODB_ERR_INVALID_ARGUMENT;
+        if (h.in_channels < HD_KB || h.in_channels % HD_KB || h.H < 1 || h.W < 1) return KODB_ERR_UNSUPPORTED;
+        const int HW = h.H * h.W;
+        if (HW % 4) return KODB_ERR_UNSUPPORTED;  // TMA: strides are multiples of 16 bytes
+        if ((reinterpret_cast<uintptr_t>(h.x) | reinterpret_cast<uintptr_t>(h.weight)) & 15u) return KODB_ERR_INVALID_ARGUMENT;
+        HeadLevelParams& L = p.lv[l];
+        L.K = h.in_channels;
+        L.HW = HW;
+        L.B = batch;
+        L.tiles_per_image = (HW + HD_TILE_M - 1) / HD_TILE_M;
+        L.tile_begin = tiles;
+        tiles += L.tiles_per_image * batch;
+        L.n1 = num_anchors * 4;
+        L.n2 = L.n1 + num_anchors;
+        L.n3 = n3;
+        L.out[0] = h.out_box; L.out[1] = h.out_obj; L.out[2] = h.out_cls;
+        L.bias[0] = h.bias_box; L.bias[1] = h.bias_obj; L.bias[2] = h.bias_cls;
+        {   // feature map (B, K, H, W) as (cell, channel, image)
+            const cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)h.in_channels, (cuuint64_t)batch};
+            const cuuint64_t strides[2] = {(cuuint64_t)HW * 4, (cuuint64_t)HW * 4 * h.in_channels};
+            const cuuint32_t box[3] = {32, (cuuint32_t)HD_KB, 1};
+            const cuuint32_t estr[3] = {1, 1, 1};
+            if (encode(&p.tma_x[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(h.x), dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, (CUtensorMapSwizzle)x_swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return KODB_ERR_INVALID_ARGUMENT;
+        }
+        {   // concatenated weights (n, K) as (channel, n); rows beyond n3 are out of bounds -> zeros
+            const cuuint64_t dims[2] = {(cuuint64_t)h.in_channels, (cuuint64_t)n3};
+            const cuuint64_t strides[1] = {(cuuint64_t)h.in_channels * 4};
+            const cuuint32_t box[2] = {(cuuint32_t)HD_KB, (cuuint32_t)n_pad};
+            const cuuint32_t estr[2] = {1, 1};
+            if (encode(&p.tma_w[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(h.weight), dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return KODB_ERR_INVALID_ARGUMENT;
+        }
+    }
+    p.total_tiles = tiles;
+    for (int l = num_levels; l < KODB_NUM_LEVELS; ++l) {  // absent levels own no tiles
+        p.lv[l] = HeadLevelParams{};
+        p.lv[l].tile_begin = tiles;
+        p.tma_x[l] = p.tma_x[0];
+        p.tma_w[l] = p.tma_w[0];
+    }
+    const size_t smem = 1024 + (size_t)HD_STAGES * (HD_A_STAGE_BYTES + p.b_stage_bytes) + 256;
+    static std::mutex mu;
+    static size_t smem_set[64] = {0};
+    static int sms[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return KODB_ERR_UNSUPPORTED;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (smem_set[dev] < smem) {
+            if (cudaFuncSetAttribute(head_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+                return KODB_ERR_LAUNCH;
+            smem_set[dev] = smem;
+        }
+        if (!sms[dev]) {
+            int n = 0;
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+            sms[dev] = n > 0 ? n : 148;
+        }
+    }
+    // persistent: as many CTAs as fit (shared memory: two per SM with the small class head, one with 80 classes)
+    const int per_sm = smem <= 110 * 1024 ? 2 : 1;
+    int grid = sms[dev] * per_sm;
+    if (grid > tiles) grid = tiles;
+    head_forward_kernel<<<grid, HD_THREADS, smem, (cudaStream_t)stream>>>(p);
+    KODB_CHECK_LAUNCH();
+    return KODB_OK;
+}

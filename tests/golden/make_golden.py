@@ -507,8 +507,41 @@ def augment_cases():
     save("augment_boxes", **out)
 
 
+# ------------------------------------------------------------------------------------------------
+# Detect head: the three 1x1 convs + Rearrange of kod/nn/heads/yolov5.py, forward + backward
+# ------------------------------------------------------------------------------------------------
+def head_cases():
+    from kod.nn.heads.yolov5 import Yolov5Head
+    out = {}
+    B, C, A = 2, 10, 3
+    g = torch.Generator().manual_seed(91)
+    cfgs = [(64, 16, 16, 8), (128, 12, 12, 16), (256, 6, 6, 32)]  # (in_channels, H, W, stride); 6x6 = 36 cells: ragged tile
+    out["meta"] = np.array([B, C, A], np.int64)
+    out["cfgs"] = np.array(cfgs, np.int64)
+    for l, (K, Hh, Ww, stride) in enumerate(cfgs):
+        torch.manual_seed(92 + l)
+        head = Yolov5Head(in_channels=K, num_anchors_per_cell=A, num_classes=C, stride=stride)
+        x = torch.randn(B, K, Hh, Ww, generator=g).requires_grad_(True)
+        r = head(x)
+        ups = [torch.randn(t.shape, generator=g) for t in r]
+        sum((t * u).sum() for t, u in zip(r, ups)).backward()
+        out[f"l{l}/x"] = x.detach().numpy()
+        out[f"l{l}/dx"] = x.grad.numpy()
+        for name, p in head.state_dict().items():
+            out[f"l{l}/param/{name}"] = p.numpy()
+        for name, p in head.named_parameters():
+            out[f"l{l}/grad/{name}"] = p.grad.numpy()
+        for part, t, u in zip(("box", "obj", "cls"), r, ups):
+            out[f"l{l}/{part}"] = t.detach().numpy()  # (B, A, H, W, P)
+            out[f"l{l}/up_{part}"] = u.numpy()
+    save("head_convs", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "head":
+        head_cases()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "augment":
         augment_cases()
         sys.exit(0)
@@ -529,3 +562,4 @@ if __name__ == "__main__":
     iou_cases()
     sgd_cases()
     augment_cases()
+    head_cases()
