@@ -16,7 +16,6 @@
 //     cells of ONE output plane, which is precisely the planar layout the detection tail wants).
 // HBM-bound by construction (AI ~ 17 flop/B at K=128, N=45): 4*K bytes in + 4*N bytes out per cell.
 #include <cuda.h>  // CUtensorMap + enums only; the encoder entry point is fetched at run time (no libcuda link dependency)
-#include <stdio.h>
 #include <stdlib.h>
 
 #include <mutex>
@@ -29,12 +28,24 @@ constexpr int HD_TILE_M = 128;   // cells per tile (UMMA M)
 constexpr int HD_KB = 32;        // channels per pipeline stage (one 128-byte swizzle row of fp32)
 constexpr int HD_UMMA_K = 8;     // tf32: 32 bytes of K per instruction
 constexpr int HD_STAGES = 4;
-constexpr int HD_THREADS = 192;  // 6 warps: TMA, MMA, 4 x epilogue
+constexpr int HD_EPI_WARPS = 8;  // two per TMEM lane quadrant: even / odd 16-column chunks
+constexpr int HD_THREADS = 32 * (2 + HD_EPI_WARPS);  // warps: TMA, MMA, 8 x epilogue
+constexpr int HD_UNIT_KB = 16;   // scheduling unit: tiles worth 16 k-blocks of loads (4 tiles at K=128, 2 at 256, 1 at >= 512)
 constexpr int HD_A_STAGE_BYTES = HD_TILE_M * HD_KB * 4;  // 16 KB: four slabs of 32 cells x 32 channels
+constexpr int HD_A_SBO = 512;    // A operand: bytes between two 4-channel swizzle atoms
+constexpr int HD_A_KADV = 1024;  // A operand: bytes per MMA (8 channels)
+
+// where one output channel of a level goes: base = its plane in image 0, images img_stride elements apart
+struct __align__(16) HeadChannel {
+    float* base;
+    uint32_t img_stride;
+    float bias;
+};
 
 struct HeadLevelParams {
     int K, HW, B;
-    int tiles_per_image, tile_begin;
+    int tiles_per_image, tiles;
+    int unit_begin, per_unit;  // this level's scheduling units start at unit_begin; per_unit tiles each
     int n1, n2, n3;      // channel boundaries: box [0, n1), objectness [n1, n2), class [n2, n3)
     float* out[3];       // planar [B][channels][HW]
     const float* bias[3];
@@ -47,8 +58,8 @@ struct HeadParams {
     int n_pad;           // UMMA N: A*(5+C) rounded up to 16
     int acc_cols;        // TMEM columns per accumulator (power of two >= n_pad)
     int b_stage_bytes;   // n_pad * 128
-    int total_tiles;
-    uint32_t a_layout, a_lbo, a_sbo, a_kadv;  // A-operand descriptor fields
+    int total_units;
+    int order[KODB_NUM_LEVELS];  // levels by descending K: the heavy tiles lead the static round-robin
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------------
@@ -122,7 +133,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, leading / stride byte offsets in
 // 16-byte units, version 1 (sm_100), layout type SWIZZLE_128B
-__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = 2) {
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
@@ -133,6 +144,11 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t 
 }
 
 // =========================================================================================================
+// scheduling units in the order levels are listed in p.order (descending K); unit u -> level, tiles [t0, t1)
+__device__ __forceinline__ int unit_level(const HeadParams& p, int u) {
+    return u >= p.lv[p.order[2]].unit_begin ? p.order[2] : (u >= p.lv[p.order[1]].unit_begin ? p.order[1] : p.order[0]);
+}
+
 __global__ void __launch_bounds__(HD_THREADS, 1) head_forward_kernel(const __grid_constant__ HeadParams p) {
     extern __shared__ __align__(1024) uint8_t hd_smem_raw[];
     // 1024-byte alignment of every operand stage (128B swizzle atoms are 1 KB)
@@ -145,6 +161,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_forward_kernel(const __gri
     uint64_t* tfull_bar = bars + 2 * HD_STAGES;   // [2]          MMA -> epilogue
     uint64_t* tempty_bar = bars + 2 * HD_STAGES + 2;  // [2]      epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * HD_STAGES + 4);
+    HeadChannel* chan = reinterpret_cast<HeadChannel*>(bars + 2 * HD_STAGES + 6);  // [KODB_NUM_LEVELS][n_pad]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -159,7 +176,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_forward_kernel(const __gri
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar + a, 1);
-            mbar_init(tempty_bar + a, 4);  // one arrival per epilogue warp
+            mbar_init(tempty_bar + a, HD_EPI_WARPS);  // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -167,6 +184,21 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_forward_kernel(const __gri
         const uint32_t ncols = 2u * (uint32_t)p.acc_cols;
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // the output channel table: the epilogue's whole address computation is one 16-byte shared-memory read per store
+    for (int i = threadIdx.x; i < KODB_NUM_LEVELS * p.n_pad; i += HD_THREADS) {
+        const int l = i / p.n_pad, n = i - l * p.n_pad;
+        const HeadLevelParams& L = p.lv[l];
+        HeadChannel c{nullptr, 0u, 0.f};
+        if (L.tiles > 0 && n < L.n3) {
+            const int ti = n < L.n1 ? 0 : (n < L.n2 ? 1 : 2);
+            const int nb = ti == 0 ? 0 : (ti == 1 ? L.n1 : L.n2);
+            const int ch = ti == 0 ? L.n1 : (ti == 1 ? L.n2 - L.n1 : L.n3 - L.n2);
+            c.base = L.out[ti] + (size_t)(n - nb) * L.HW;
+            c.img_stride = (uint32_t)(ch * L.HW);
+            c.bias = __ldg(L.bias[ti] + (n - nb));
+        }
+        chan[i] = c;
     }
     tc_fence_before();
     __syncthreads();
@@ -179,20 +211,22 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_forward_kernel(const __gri
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t tx = (uint32_t)(HD_A_STAGE_BYTES + p.b_stage_bytes);
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-                const int l = t >= p.lv[2].tile_begin ? 2 : (t >= p.lv[1].tile_begin ? 1 : 0);
+            for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+                const int l = unit_level(p, u);
                 const HeadLevelParams& L = p.lv[l];
-                const int tt = t - L.tile_begin;
-                const int b = tt / L.tiles_per_image, c0 = (tt - b * L.tiles_per_image) * HD_TILE_M;
-                for (int kb = 0; kb < L.K / HD_KB; ++kb) {
-                    mbar_wait(empty_bar + stage, phase ^ 1u);
-                    mbar_expect_tx(full_bar + stage, tx);
-                    uint8_t* a_dst = smem_a + stage * HD_A_STAGE_BYTES;
+                const int t0 = (u - L.unit_begin) * L.per_unit, t1 = min(t0 + L.per_unit, L.tiles);
+                for (int tt = t0; tt < t1; ++tt) {
+                    const int b = tt / L.tiles_per_image, c0 = (tt - b * L.tiles_per_image) * HD_TILE_M;
+                    for (int kb = 0; kb < L.K / HD_KB; ++kb) {
+                        mbar_wait(empty_bar + stage, phase ^ 1u);
+                        mbar_expect_tx(full_bar + stage, tx);
+                        uint8_t* a_dst = smem_a + stage * HD_A_STAGE_BYTES;
 #pragma unroll
-                    for (int j = 0; j < HD_TILE_M / 32; ++j)  // slab j: cells c0 + 32j .. + 31 (zero-filled beyond H*W)
-                        tma_load_3d(a_dst + j * (HD_KB * 128), &p.tma_x[l], full_bar + stage, c0 + 32 * j, kb * HD_KB, b);
-                    tma_load_2d(smem_b + stage * p.b_stage_bytes, &p.tma_w[l], full_bar + stage, kb * HD_KB, 0);
-                    if (++stage == HD_STAGES) { stage = 0; phase ^= 1u; }
+                        for (int j = 0; j < HD_TILE_M / 32; ++j)  // slab j: cells c0 + 32j .. + 31 (zero-filled beyond H*W)
+                            tma_load_3d(a_dst + j * (HD_KB * 128), &p.tma_x[l], full_bar + stage, c0 + 32 * j, kb * HD_KB, b);
+                        tma_load_2d(smem_b + stage * p.b_stage_bytes, &p.tma_w[l], full_bar + stage, kb * HD_KB, 0);
+                        if (++stage == HD_STAGES) { stage = 0; phase ^= 1u; }
+                    }
                 }
             }
         }
@@ -204,74 +238,94 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_forward_kernel(const __gri
                                    ((uint32_t)(HD_TILE_M >> 4) << 24);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-                const int l = t >= p.lv[2].tile_begin ? 2 : (t >= p.lv[1].tile_begin ? 1 : 0);
-                const int nkb = p.lv[l].K / HD_KB;
-                mbar_wait(tempty_bar + acc, acc_phase ^ 1u);  // the epilogue has drained this accumulator
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_cols);
-                for (int kb = 0; kb < nkb; ++kb) {
-                    mbar_wait(full_bar + stage, phase);
+            for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+                const int l = unit_level(p, u);
+                const HeadLevelParams& L = p.lv[l];
+                const int t0 = (u - L.unit_begin) * L.per_unit, t1 = min(t0 + L.per_unit, L.tiles);
+                const int nkb = L.K / HD_KB;
+                for (int tt = t0; tt < t1; ++tt) {
+                    mbar_wait(tempty_bar + acc, acc_phase ^ 1u);  // the epilogue has drained this accumulator
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem_a + stage * HD_A_STAGE_BYTES);
-                    const uint32_t b_addr = smem_u32(smem_b + stage * p.b_stage_bytes);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_cols);
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        mbar_wait(full_bar + stage, phase);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(smem_a + stage * HD_A_STAGE_BYTES);
+                        const uint32_t b_addr = smem_u32(smem_b + stage * p.b_stage_bytes);
 #pragma unroll
-                    for (int k = 0; k < HD_KB / HD_UMMA_K; ++k) {
-                        // A (MN-major): slabs of 32 cells are HD_KB*128 bytes apart (LBO), groups of 8 channel rows 1 KB (SBO);
-                        //   one instruction consumes one group -> advance by 1 KB.
-                        // B (K-major): rows of 128 bytes, 8-row groups 1 KB apart (SBO); 8 channels = 32 bytes along the row.
-                        const uint64_t a_desc = umma_smem_desc(a_addr + k * p.a_kadv, p.a_lbo, p.a_sbo, p.a_layout);
-                        const uint64_t b_desc = umma_smem_desc(b_addr + k * 32, 16, 1024);
-                        umma_tf32(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < HD_KB / HD_UMMA_K; ++k) {
+                            // A (MN-major, 128B swizzle / 32B atom): atoms of 4 channel rows x 128 B; one instruction takes 8
+                            //   channels = 2 atoms HD_A_SBO apart; the four 32-cell slabs are HD_KB*128 bytes apart (LBO).
+                            // B (K-major, 128B swizzle): rows of 128 bytes, 8-row groups 1 KB apart (SBO); 8 channels = 32
+                            //   bytes along the row.
+                            const uint64_t a_desc = umma_smem_desc(a_addr + k * HD_A_KADV, HD_KB * 128, HD_A_SBO, 1);
+                            const uint64_t b_desc = umma_smem_desc(b_addr + k * 32, 16, 1024, 2);
+                            umma_tf32(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
+                        umma_commit(empty_bar + stage);  // the stage's operands may be overwritten once these MMAs are done
+                        if (kb == nkb - 1) umma_commit(tfull_bar + acc);  // ... and the accumulator is complete
+                        if (++stage == HD_STAGES) { stage = 0; phase ^= 1u; }
                     }
-                    umma_commit(empty_bar + stage);  // the stage's operands may be overwritten once these MMAs are done
-                    if (kb == nkb - 1) umma_commit(tfull_bar + acc);  // ... and the accumulator is complete
-                    if (++stage == HD_STAGES) { stage = 0; phase ^= 1u; }
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
                 }
-                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
     } else {
         // ===== epilogue: TMEM -> registers -> (+ bias) -> planar global stores =====
-        const int q = warp & 3;  // the TMEM lane quadrant this warp may read
+        const int q = warp & 3;             // the TMEM lane quadrant this warp may read
+        const int half = (warp - 2) >> 2;   // 16-column chunks: even ones to the first warp of the quadrant, odd to the second
         const int row = 32 * q + lane;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-            const int l = t >= p.lv[2].tile_begin ? 2 : (t >= p.lv[1].tile_begin ? 1 : 0);
+        for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+            const int l = unit_level(p, u);
             const HeadLevelParams& L = p.lv[l];
-            const int tt = t - L.tile_begin;
-            const int b = tt / L.tiles_per_image, c0 = (tt - b * L.tiles_per_image) * HD_TILE_M;
-            const int cell = c0 + row;
-            mbar_wait(tfull_bar + acc, acc_phase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * p.acc_cols);
-            for (int n0 = 0; n0 < L.n3; n0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(taddr + n0, v);
-                tmem_ld_wait();
-                if (n0 + 16 >= L.n3) {
-                    // last chunk read: hand the accumulator back before the stores go out
+            const int t0 = (u - L.unit_begin) * L.per_unit, t1 = min(t0 + L.per_unit, L.tiles);
+            const HeadChannel* tab = chan + l * p.n_pad;
+            const int n3 = L.n3;
+            for (int tt = t0; tt < t1; ++tt) {
+                const int b = tt / L.tiles_per_image, c0 = (tt - b * L.tiles_per_image) * HD_TILE_M;
+                const int cell = c0 + row;
+                const bool live = cell < L.HW;
+                mbar_wait(tfull_bar + acc, acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * p.acc_cols);
+                int n0 = 16 * half;
+                if (n0 >= n3) {  // nothing to read for this warp: hand the accumulator back at once
                     tc_fence_before();
-                    __syncwarp();
                     if (lane == 0) mbar_arrive(tempty_bar + acc);
                 }
-                if (cell < L.HW) {
+                for (; n0 < n3; n0 += 32) {
+                    uint32_t v[16];
+                    tmem_ld16(taddr + n0, v);
+                    tmem_ld_wait();
+                    if (n0 + 32 >= n3) {
+                        // this warp's last chunk is in registers: hand the accumulator back before the stores go out
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty_bar + acc);
+                    }
+                    if (live) {
+                        if (n0 + 16 <= n3) {
 #pragma unroll
-                    for (int u = 0; u < 16; ++u) {
-                        const int n = n0 + u;
-                        if (n < L.n3) {
-                            const int ti = n < L.n1 ? 0 : (n < L.n2 ? 1 : 2);
-                            const int nb = ti == 0 ? 0 : (ti == 1 ? L.n1 : L.n2);
-                            const int ch = ti == 0 ? L.n1 : (ti == 1 ? L.n2 - L.n1 : L.n3 - L.n2);
-                            const float bias = __ldg(L.bias[ti] + (n - nb));
-                            // 32 lanes -> 32 consecutive cells of one output plane: a 128-byte store
-                            L.out[ti][((size_t)b * ch + (n - nb)) * L.HW + cell] = __uint_as_float(v[u]) + bias;
+                            for (int i = 0; i < 16; ++i) {
+                                const HeadChannel c = tab[n0 + i];  // one broadcast 16-byte read
+                                // 32 lanes -> 32 consecutive cells of one output plane: a 128-byte store
+                                c.base[(size_t)b * c.img_stride + cell] = __uint_as_float(v[i]) + c.bias;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                if (n0 + i < n3) {
+                                    const HeadChannel c = tab[n0 + i];
+                                    c.base[(size_t)b * c.img_stride + cell] = __uint_as_float(v[i]) + c.bias;
+                                }
+                            }
                         }
                     }
                 }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
     }
     tc_fence_before();
@@ -320,16 +374,7 @@ extern "C" int kodb_head_forward(const kodb_head_conv_level* levels_h, int32_t n
     while (p.acc_cols < n_pad) p.acc_cols *= 2;
     p.b_stage_bytes = n_pad * 128;
     // A operand (MN-major tf32): the only legal shared-memory layout is the 128-byte swizzle with a 32-byte atom
-    // (cutlass sm100_common.inl:92) -- atoms of 4 channel rows x 128 B; 8 channels per instruction = 2 atoms (SBO 512 B
-    // apart); 32-cell slabs HD_KB*128 bytes apart (LBO)
-    int x_swizzle = (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-    p.a_layout = 1; p.a_lbo = HD_KB * 128; p.a_sbo = 512; p.a_kadv = 1024;
-    if (const char* dbg = getenv("KODB_HD_DBG")) {  // probing aid: "swizzle,layout,lbo,sbo,kadv"
-        int v[5];
-        if (sscanf(dbg, "%d,%d,%d,%d,%d", v, v + 1, v + 2, v + 3, v + 4) == 5) {
-            x_swizzle = v[0]; p.a_layout = v[1]; p.a_lbo = v[2]; p.a_sbo = v[3]; p.a_kadv = v[4];
-        }
-    }
+    // (cutlass sm100_common.inl:92; UMMA layout type SWIZZLE_128B_BASE32B)
     int tiles = 0;
     for (int l = 0; l < num_levels; ++l) {
         const kodb_head_conv_level& h = levels_h[l];
@@ -344,8 +389,9 @@ extern "C" int kodb_head_forward(const kodb_head_conv_level* levels_h, int32_t n
         L.HW = HW;
         L.B = batch;
         L.tiles_per_image = (HW + HD_TILE_M - 1) / HD_TILE_M;
-        L.tile_begin = tiles;
-        tiles += L.tiles_per_image * batch;
+        L.tiles = L.tiles_per_image * batch;
+        L.per_unit = HD_UNIT_KB / (L.K / HD_KB) > 0 ? HD_UNIT_KB / (L.K / HD_KB) : 1;
+        tiles += L.tiles;
         L.n1 = num_anchors * 4;
         L.n2 = L.n1 + num_anchors;
         L.n3 = n3;
@@ -357,7 +403,7 @@ extern "C" int kodb_head_forward(const kodb_head_conv_level* levels_h, int32_t n
             const cuuint32_t box[3] = {32, (cuuint32_t)HD_KB, 1};
             const cuuint32_t estr[3] = {1, 1, 1};
             if (encode(&p.tma_x[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(h.x), dims, strides, box, estr,
-                       CU_TENSOR_MAP_INTERLEAVE_NONE, (CUtensorMapSwizzle)x_swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
                 return KODB_ERR_INVALID_ARGUMENT;
         }
@@ -372,14 +418,25 @@ extern "C" int kodb_head_forward(const kodb_head_conv_level* levels_h, int32_t n
                 return KODB_ERR_INVALID_ARGUMENT;
         }
     }
-    p.total_tiles = tiles;
     for (int l = num_levels; l < KODB_NUM_LEVELS; ++l) {  // absent levels own no tiles
         p.lv[l] = HeadLevelParams{};
-        p.lv[l].tile_begin = tiles;
         p.tma_x[l] = p.tma_x[0];
         p.tma_w[l] = p.tma_w[0];
     }
-    const size_t smem = 1024 + (size_t)HD_STAGES * (HD_A_STAGE_BYTES + p.b_stage_bytes) + 256;
+    // scheduling units, heavy levels first
+    for (int l = 0; l < KODB_NUM_LEVELS; ++l) p.order[l] = l;
+    for (int i = 0; i < KODB_NUM_LEVELS; ++i)
+        for (int j = i + 1; j < KODB_NUM_LEVELS; ++j)
+            if (p.lv[p.order[j]].K > p.lv[p.order[i]].K) { const int t = p.order[i]; p.order[i] = p.order[j]; p.order[j] = t; }
+    int units = 0;
+    for (int i = 0; i < KODB_NUM_LEVELS; ++i) {
+        HeadLevelParams& L = p.lv[p.order[i]];
+        L.unit_begin = units;
+        if (L.tiles > 0) units += (L.tiles + L.per_unit - 1) / L.per_unit;
+    }
+    p.total_units = units;
+    const size_t smem = 1024 + (size_t)HD_STAGES * (HD_A_STAGE_BYTES + p.b_stage_bytes) + 256 +
+                        (size_t)KODB_NUM_LEVELS * n_pad * sizeof(HeadChannel);
     static std::mutex mu;
     static size_t smem_set[64] = {0};
     static int sms[64] = {0};
@@ -402,7 +459,7 @@ extern "C" int kodb_head_forward(const kodb_head_conv_level* levels_h, int32_t n
     // persistent: as many CTAs as fit (shared memory: two per SM with the small class head, one with 80 classes)
     const int per_sm = smem <= 110 * 1024 ? 2 : 1;
     int grid = sms[dev] * per_sm;
-    if (grid > tiles) grid = tiles;
+    if (grid > units) grid = units;
     head_forward_kernel<<<grid, HD_THREADS, smem, (cudaStream_t)stream>>>(p);
     KODB_CHECK_LAUNCH();
     return KODB_OK;
