@@ -617,6 +617,12 @@ def run_ours(a):
                 torch.cuda.empty_cache()
             except Exception as e:  # pragma: no cover
                 extra[key] = {"workload": c["name"], "error": str(e)[:200]}
+        for key, (hb, hs, hc) in {"f1_detect_head": (B, S, Cn), "f1_detect_head_1280_c80": (8, 1280, 80)}.items():
+            try:
+                extra[key] = measure_head(hb, hs, hc, peak)
+                torch.cuda.empty_cache()
+            except Exception as e:  # pragma: no cover
+                extra[key] = {"error": f"{type(e).__name__}: {e}"[:200]}
 
     if rank == 0:
         ac = sum(3 * (S // s) ** 2 for s in (8, 16, 32))
@@ -669,6 +675,73 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+def measure_head(B, S, Cn, peak, n=20, nsets=3):
+    """the Detect head (three 1x1 convolutions per level + Rearrange) as ONE tcgen05 launch
+    (`kodb_head_forward`) against the reference's own execution -- nine cuDNN convolutions through torch -- on the same
+    inputs; device time per call, n calls over `nsets` rotating input sets (> L2 together) in one CUDA graph."""
+    import torch
+    import torch.nn.functional as F
+
+    from object_detection_cib_b200.heads import Yolov5Head, fused_heads_forward
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    cfg = ((128, 8), (256, 16), (512, 32))
+    torch.manual_seed(0)
+    heads = [Yolov5Head(K, 3, Cn, s).to(dev) for K, s in cfg]
+    xsets = [[torch.randn(B, K, S // s, S // s, device=dev) for K, s in cfg] for _ in range(nsets)]
+
+    def ref(xs):
+        return [[F.conv2d(x, m.conv.weight, m.conv.bias) for m in (h.box_head, h.obj_head, h.cls_head)] for h, x in zip(heads, xs)]
+
+    def timed(fn):
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            for i in range(3):
+                fn(xsets[i % nsets])
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=st):
+                for i in range(n):
+                    fn(xsets[i % nsets])
+            g.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    old = torch.backends.cudnn.allow_tf32
+    try:
+        with torch.no_grad():
+            t_ours = timed(lambda xs: fused_heads_forward(heads, xs))
+            torch.backends.cudnn.allow_tf32 = True
+            t_tf32 = timed(ref)
+            torch.backends.cudnn.allow_tf32 = False
+            t_fp32 = timed(ref)
+            got, want = fused_heads_forward(heads, xsets[0]), ref(xsets[0])
+            err = max(float((g.permute(0, 1, 4, 2, 3).reshape(w.shape) - w).abs().max()) for gl, wl in zip(got, want) for g, w in zip(gl, wl))
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    n_out = 3 * (5 + Cn)
+    cells = sum((S // s) ** 2 for _, s in cfg)
+    b_in = sum(4 * B * K * (S // s) ** 2 for K, s in cfg)
+    b_out = 4 * B * n_out * cells
+    ach = (b_in + b_out) / (t_ours * 1e-3) / 1e9
+    return {"workload": f"Detect head, {B} img {S}x{S}, {Cn} classes: box/obj/cls 1x1 convolutions of the three pyramid levels "
+                        f"(K = 128/256/512 -> {n_out} channels) + planar Rearrange, fp32 in, tf32 multiply, fp32 accumulate",
+            "kernel": "head_forward_kernel (tcgen05.mma kind::tf32, TMEM accumulators, TMA loads; one launch for all levels)",
+            "ms_per_call": t_ours, "value": B / (t_ours * 1e-3), "unit": UNIT, "gpu_launches_per_call": 1,
+            "cudnn_tf32_ms_per_call": t_tf32, "cudnn_fp32_ms_per_call": t_fp32, "cudnn_launches_per_call": 9,
+            "speedup_vs_cudnn_tf32": t_tf32 / t_ours, "speedup_vs_cudnn_fp32": t_fp32 / t_ours,
+            "max_abs_err_vs_fp32_conv": err,
+            "roofline": {"bound": "hbm", "kernel": "head_forward_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "algorithmic_bytes_per_launch": b_in + b_out,
+                         "note": "4*K bytes in + 4*3*(5+C) bytes out per cell; ~17 flop/B at K=128: HBM-bound, the tensor "
+                                 "cores only have to keep up"}}
+
+
 def wl_launches(steps):
     return 3 * steps  # train_tail_kernel, cand_floor_kernel, select_nms_kernel per step
 
@@ -719,25 +792,90 @@ def _nms_backend():
 
 
 def cpu_baseline(a, n_img):
+    """The reference's CPU path on a bounded sample of the step's workload: its own files from oracle/_ref when staged
+    (kind "reference"), else the oracle port (kind "port")."""
     import torch
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     backend = _nms_backend()
     heads, targets = _cpu_inputs(a, n_img)
+    R = None
+    try:
+        R = _ref_modules()
+    except Exception:  # pragma: no cover
+        R = None
     t0 = time.perf_counter()
-    _cpu_step(a, heads, targets, backend)
+    if R:
+        _ref_step(a, R, heads, targets)
+    else:
+        _cpu_step(a, heads, targets, backend)
     dt = time.perf_counter() - t0
-    return {"value": n_img / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{n_img} images of the step's workload (oracle port: assign + loss fwd/bwd via torch CPU "
-                      f"autograd, decode, {backend} greedy NMS conf 0.001 / IoU 0.6, COCO matching), {dt:.1f} s",
-            "seconds": dt}
+    what = ("the reference's own Yolov5Loss fwd+bwd, get_detections, non_max_suppression (oracle/_ref) on torch CPU; COCO "
+            "matching by the oracle's restatement") if R else \
+           f"oracle port: assign + loss fwd/bwd via torch CPU autograd, decode, {backend} greedy NMS conf 0.001 / IoU 0.6, COCO matching"
+    return {"value": n_img / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "reference" if R else "port",
+            "sample": f"{n_img} images of the step's workload ({what}), {dt:.1f} s", "seconds": dt}
+
+
+def _ref_modules():
+    """The reference's own modules from oracle/_ref (staged by build(), see oracle/ref_stage.py), or None."""
+    from oracle import ref_stage
+
+    if not ref_stage.staged() or not ref_stage.install(ref_stage.STAGED_ROOT):
+        return None
+    from kod.core.anchors.info import AnchorBoxInfo
+    from kod.core.bbox.iou import IoUCalculator, IoUType
+    from kod.core.label_assignment.yv5 import AssignmentAnchorInfo, Yolov5LabelAssigner
+    from kod.core.nms import non_max_suppression
+    from kod.core.types import FeatureShape
+    from kod.data.detection import DetectionTarget
+    from kod.lightning.experiments.yv5_baseline.exp import DefaultYolov5Experiment
+    from kod.lightning.experiments.yv5_baseline.loss import Yolov5Loss, Yolov5LossParams
+    from kod.lightning.experiments.yv5_baseline.type_defs import LayerwiseAnchorInfo
+    from kod.nn.heads.types import DetectionHeadResult
+    from kod.nn.networks.yolov5 import Yolov5NetworkResult
+
+    return dict(locals())
+
+
+def _ref_step(a, R, heads, targets):
+    """One pass of the REAL reference over `heads`: Yolov5Loss forward + backward (loss.py:46-248, exp.py:124-130),
+    get_detections (exp.py:70-102), non_max_suppression (nms.py:9-75); the COCO matching is third-party code that is
+    absent here (pycocotools behind vision_evaluation): the oracle's restatement stands in for it."""
+    import torch
+
+    from object_detection_cib_b200 import synthetic as syn
+    from oracle import coco_map as om
+
+    S, n = a.img, heads[0][0].shape[0]
+    infos = [R["AnchorBoxInfo"](stride=s, boxes_wh=[R["FeatureShape"](width=w, height=h) for (w, h) in an])
+             for s, an in zip(syn.STRIDES, syn.ANCHORS_PX)]
+    w = syn.readme_class_weights() if a.classes == 10 else None
+    loss_mod = R["Yolov5Loss"](R["Yolov5LabelAssigner"](R["AssignmentAnchorInfo"](*infos)), R["Yolov5LossParams"].get_default(),
+                               R["IoUCalculator"](R["IoUType"]("ciou"), eps=1e-7), weights=w)
+    leaves = R["Yolov5NetworkResult"](*[R["DetectionHeadResult"](*[t.detach().clone().requires_grad_(True) for t in lv])
+                                        for lv in heads])
+    tg = tuple(R["DetectionTarget"](boxes=b, labels=l) for b, l in targets)
+    shape = R["FeatureShape"](width=S, height=S)
+    res = loss_mod(shape, leaves, tg)
+    (n * (res.localization + res.classification + res.objectness)).backward()
+
+    class _Exp:  # only what get_detections touches
+        anchor_info = R["LayerwiseAnchorInfo"](*infos)
+        get_detections = R["DefaultYolov5Experiment"].get_detections
+
+    with torch.no_grad():
+        det = _Exp().get_detections(shape, R["Yolov5NetworkResult"](*[R["DetectionHeadResult"](*lv) for lv in heads]))
+        out = R["non_max_suppression"](det, conf_thres=0.001, nms_thres=0.6)
+    for r, (gb, gl) in zip(out, targets):
+        om.match_image(r.numpy().reshape(-1, 6), gb.numpy(), gl.numpy(), a.classes)
 
 
 def run_reference(a):
-    """Reference arm: the reference's own CPU implementation of the path.  The reference is pure Python
-    (no compiled path, nothing to build into oracle/_ref) and /root/reference does not travel to the GPU
-    box, so this times the oracle port: the same ATen ops through torch CPU + torchvision's CPU NMS."""
+    """Reference arm: the reference's own CPU implementation of the path on this box's host cores -- its unmodified
+    python files from oracle/_ref (staged by build() where /root/reference exists; the reference has no compiled code),
+    else the oracle port (same ATen ops through torch CPU + torchvision's CPU NMS)."""
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     if rank != 0:
@@ -747,28 +885,37 @@ def run_reference(a):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     backend = _nms_backend()
+    R = None
+    try:
+        R = _ref_modules()
+    except Exception as e:  # pragma: no cover - a broken staging falls back to the port, and says so
+        print(f"[bench] oracle/_ref not usable ({type(e).__name__}: {e}); timing the oracle port", file=sys.stderr)
+    kind = "reference" if R else "port"
+    step = (lambda h, t: _ref_step(a, R, h, t)) if R else (lambda h, t: _cpu_step(a, h, t, backend))
     total = a.steps + a.warmup
     n_img = 2 if total <= 12 else 1  # bounded sample: ~1.5-3 s of CPU work per image (O(n^2) NMS)
     heads, targets = _cpu_inputs(a, n_img)
     for _ in range(min(a.warmup, 1)):  # the CPU path has no warm-up effect worth more than one pass
-        _cpu_step(a, heads, targets, backend)
+        step(heads, targets)
     t0 = time.perf_counter()
     done = 0
     for _ in range(a.steps):
-        _cpu_step(a, heads, targets, backend)
+        step(heads, targets)
         done += 1
         if time.perf_counter() - t0 > 240 and done >= 3:  # keep the whole run within a few minutes
             break
     dt = time.perf_counter() - t0
     value = n_img * done / dt
-    sample = (f"{n_img} image(s) per step of the {a.batch}-image batch, {done} of {a.steps} requested steps timed "
-              f"(oracle port on torch CPU, {backend} NMS)")
+    what = ("the reference's own Yolov5Loss fwd+bwd, get_detections and non_max_suppression from oracle/_ref on torch CPU; "
+            "COCO matching by the oracle's restatement of pycocotools (third party, absent)") if R else \
+           f"oracle port on torch CPU, {backend} NMS"
+    sample = f"{n_img} image(s) per step of the {a.batch}-image batch, {done} of {a.steps} requested steps timed ({what})"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": done,
         "warmup": min(a.warmup, 1), "ms_per_step": dt / done * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "images_per_step": n_img, "img": a.img, "classes": a.classes},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

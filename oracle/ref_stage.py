@@ -1,0 +1,93 @@
+"""oracle/_ref: the reference's OWN python files of the hot path, staged for the `--impl reference` arm of bench.py.
+
+TEST / MEASUREMENT INFRASTRUCTURE, NOT PRODUCT CODE.  The reference (craston/object_detection_cib, package `kod`) is
+pure Python: there is nothing to compile, so "building" oracle/_ref is `stage()` -- the `kod` package is copied
+UNMODIFIED from /root/reference into oracle/_ref/kod.  oracle/_ref/ is git-ignored (no reference source enters the
+history) but not gpurun-ignored, so the GPU box -- which has no /root/reference -- can time the real
+`Yolov5Loss` (kod/lightning/experiments/yv5_baseline/loss.py:46-248), `DefaultYolov5Experiment.get_detections`
+(exp.py:70-102) and `non_max_suppression` (kod/core/nms.py:9-75) on its host cores.
+
+`install(root)` makes `import kod` work from a reference tree: `sys.modules` stubs for the packages `kod` imports at
+module level but does not execute on this path (albumentations, lightning, vision_evaluation: SURVEY.md Appendix C).
+`__graft_entry__.build()` calls `stage()` where /root/reference exists; `tests/golden/make_golden.py` uses `install()`
+on /root/reference itself.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import sys
+import types
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+STAGED_ROOT = os.path.join(HERE, "_ref")
+REFERENCE_ROOT = os.environ.get("KOD_REFERENCE_ROOT", "/root/reference")
+
+
+def stage(src_root: str = REFERENCE_ROOT, dst_root: str = STAGED_ROOT) -> bool:
+    """Copy the python files of `<src_root>/kod` to `<dst_root>/kod`.  False when the reference is absent."""
+    src = os.path.join(src_root, "kod")
+    if not os.path.isdir(src):
+        return False
+    dst = os.path.join(dst_root, "kod")
+    if os.path.isdir(dst):
+        shutil.rmtree(dst)
+    shutil.copytree(src, dst, ignore=lambda d, names: [n for n in names
+                                                        if not (n.endswith(".py") or os.path.isdir(os.path.join(d, n)))
+                                                        or n == "__pycache__"])
+    return True
+
+
+def staged() -> bool:
+    return os.path.isfile(os.path.join(STAGED_ROOT, "kod", "core", "nms.py"))
+
+
+def _stub(name: str, **attrs):
+    mod = types.ModuleType(name)
+    mod.__dict__.update(attrs)
+    sys.modules[name] = mod
+    return mod
+
+
+def install(root: str) -> bool:
+    """Make `import kod...` resolve to `<root>/kod`.  Returns False when that tree is absent."""
+    if not os.path.isdir(os.path.join(root, "kod")):
+        return False
+    if "kod" in sys.modules:
+        return True
+    import torch.nn as nn
+
+    sys.dont_write_bytecode = True  # /root/reference is read-only
+
+    _stub("albumentations")
+    _stub("albumentations.pytorch", ToTensorV2=object)
+    _stub("albumentations.core")
+    _stub("albumentations.core.composition", TransformsSeqType=list)
+
+    class _LightningModule(nn.Module):
+        def log(self, *a, **k):
+            pass
+
+        def log_dict(self, *a, **k):
+            pass
+
+    lp = _stub("lightning.pytorch", LightningModule=_LightningModule, LightningDataModule=object, Trainer=object)
+    _stub("lightning", pytorch=lp, Callback=object, seed_everything=lambda *a, **k: None)
+    _stub("lightning.pytorch.callbacks", Callback=object)
+    _stub("lightning.pytorch.utilities", rank_zero_only=lambda f: f)
+    _stub("lightning.pytorch.utilities.types", STEP_OUTPUT=object)
+    _stub("lightning.pytorch.loggers", Logger=object)
+
+    class _Evaluator:  # constructible only; its arithmetic is third-party (pycocotools), absent here
+        def __init__(self, *a, **k):
+            pass
+
+    _stub("vision_evaluation")
+    _stub("vision_evaluation.evaluators", CocoMeanAveragePrecisionEvaluator=_Evaluator)
+
+    sys.path.insert(0, root)
+    return True
+
+
+if __name__ == "__main__":
+    print("staged" if stage() else "reference tree not found: nothing staged")

@@ -219,3 +219,34 @@ def test_bbiou_c_matches_numpy(oracle_lib):
     on._lib().kod_oracle_bbiou(np.ascontiguousarray(d).ctypes.data, 17, np.ascontiguousarray(g).ctypes.data, 9,
                                out.ctypes.data)
     assert np.array_equal(out, om.bbiou(d, g))
+
+
+def test_staged_reference_matches_the_port():
+    """oracle/_ref (the reference's own files, staged by build()) and the oracle port give the same losses on the
+    bench's CPU inputs: what `bench.py --impl reference` times is the path the parity tests pin."""
+    import types
+
+    import bench
+    from oracle import ref_stage
+
+    if not ref_stage.staged():
+        pytest.skip("oracle/_ref not staged (no /root/reference on this box and no snapshot of it)")
+    R = bench._ref_modules()
+    assert R is not None and R["non_max_suppression"].__module__ == "kod.core.nms"
+    a = types.SimpleNamespace(img=320, classes=10, batch=2)
+    heads, targets = bench._cpu_inputs(a, 2)
+    from object_detection_cib_b200 import synthetic as syn
+    from oracle import assign as oa
+    from oracle import loss as ol
+
+    levels = list(zip(syn.STRIDES, syn.ANCHORS_PX))
+    asg = oa.assign([(b.numpy(), l.numpy()) for b, l in targets], levels, 320, 320)
+    want, _ = ol.loss_forward_backward(heads, asg, 320, ol.LossHParams(), "ciou", 1e-7, syn.readme_class_weights(), upstream=(2, 2, 2))
+    infos = [R["AnchorBoxInfo"](stride=s, boxes_wh=[R["FeatureShape"](width=w, height=h) for (w, h) in an]) for s, an in levels]
+    mod = R["Yolov5Loss"](R["Yolov5LabelAssigner"](R["AssignmentAnchorInfo"](*infos)), R["Yolov5LossParams"].get_default(),
+                          R["IoUCalculator"](R["IoUType"]("ciou"), eps=1e-7), weights=syn.readme_class_weights())
+    nr = R["Yolov5NetworkResult"](*[R["DetectionHeadResult"](*lv) for lv in heads])
+    r = mod(R["FeatureShape"](width=320, height=320), nr, tuple(R["DetectionTarget"](boxes=b, labels=l) for b, l in targets))
+    got = [float(r.localization), float(r.objectness), float(r.classification)]
+    np.testing.assert_allclose(got, [float(v) for v in want], rtol=1e-6)
+    bench._ref_step(a, R, heads, targets)  # the timed callable runs end to end
