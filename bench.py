@@ -854,6 +854,8 @@ def _ref_step(a, R, heads, targets):
     w = syn.readme_class_weights() if a.classes == 10 else None
     loss_mod = R["Yolov5Loss"](R["Yolov5LabelAssigner"](R["AssignmentAnchorInfo"](*infos)), R["Yolov5LossParams"].get_default(),
                                R["IoUCalculator"](R["IoUType"]("ciou"), eps=1e-7), weights=w)
+    if loss_mod.weights is not None:
+        loss_mod.weights = loss_mod.weights.cpu()  # loss.py:58-61 moves them to cuda when one is visible: this is the CPU arm
     leaves = R["Yolov5NetworkResult"](*[R["DetectionHeadResult"](*[t.detach().clone().requires_grad_(True) for t in lv])
                                         for lv in heads])
     tg = tuple(R["DetectionTarget"](boxes=b, labels=l) for b, l in targets)

@@ -245,6 +245,7 @@ def test_staged_reference_matches_the_port():
     infos = [R["AnchorBoxInfo"](stride=s, boxes_wh=[R["FeatureShape"](width=w, height=h) for (w, h) in an]) for s, an in levels]
     mod = R["Yolov5Loss"](R["Yolov5LabelAssigner"](R["AssignmentAnchorInfo"](*infos)), R["Yolov5LossParams"].get_default(),
                           R["IoUCalculator"](R["IoUType"]("ciou"), eps=1e-7), weights=syn.readme_class_weights())
+    mod.weights = mod.weights.cpu()  # (loss.py:58-61 moves them to cuda when one is visible)
     nr = R["Yolov5NetworkResult"](*[R["DetectionHeadResult"](*lv) for lv in heads])
     r = mod(R["FeatureShape"](width=320, height=320), nr, tuple(R["DetectionTarget"](boxes=b, labels=l) for b, l in targets))
     got = [float(r.localization), float(r.objectness), float(r.classification)]
