@@ -36,6 +36,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "yolov5s_tail_images_per_s"
 UNIT = "images/s"
+SPLIT_CHAINS = os.environ.get("KODB_BENCH_SPLIT", "0") == "1"
 NSETS = int(os.environ.get("KODB_BENCH_NSETS", "3"))  # rotating input sets: 3 x (96.8 MB head + 96.8 MB grads) >> 126 MB L2
 
 
@@ -269,7 +270,20 @@ def capture_steps(wl, n_steps, mode, dev):
     evs = [torch.cuda.Event() for _ in range(ns)]
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g, stream=cap):
-        if mode == "pipelined":
+        if mode == "pipelined" and SPLIT_CHAINS and wl.train and wl.evalt:
+            # the train tails and the eval tails of the K steps as independent chains (they share inputs, not results)
+            cur = torch.cuda.current_stream(dev)
+            for b in branches + sides:
+                b.wait_stream(cur)
+            for i in range(n_steps):
+                st = wl.sets[i % ns]
+                with torch.cuda.stream(branches[i % ns]):
+                    wl.eval_call(st)
+                with torch.cuda.stream(sides[i % ns]):
+                    wl.train_call(st)
+            for b in branches + sides:
+                cur.wait_stream(b)
+        elif mode == "pipelined":
             cur = torch.cuda.current_stream(dev)
             for b in branches:
                 b.wait_stream(cur)

@@ -856,9 +856,34 @@ __device__ __forceinline__ void stage_gt(GtSmem& gs, int C, const void* gt_boxes
     }
 }
 
+// Ground truth of one image as the matching stage sees it: in shared memory (up to GT_CAP boxes, the fused path) or in a
+// global scratch (crowded images, match_crowded_kernel) -- same code, two storages.
+struct GtInSmem {
+    GtSmem& s;
+    __device__ __forceinline__ double gx(int g) const { return s.gx[g]; }
+    __device__ __forceinline__ double gy(int g) const { return s.gy[g]; }
+    __device__ __forceinline__ double gw(int g) const { return s.gw[g]; }
+    __device__ __forceinline__ double gh(int g) const { return s.gh[g]; }
+    __device__ __forceinline__ int glabel(int g) const { return s.glabel[g]; }
+    __device__ __forceinline__ unsigned char& taken(int t, int g) const { return s.taken[t][g]; }
+};
+struct GtInGlobal {  // [4][cap] doubles, [cap] labels, [KODB_NUM_IOU_THRS][cap] flags
+    double* xywh;
+    int* label;
+    unsigned char* flags;
+    int cap;
+    __device__ __forceinline__ double gx(int g) const { return xywh[g]; }
+    __device__ __forceinline__ double gy(int g) const { return xywh[cap + g]; }
+    __device__ __forceinline__ double gw(int g) const { return xywh[2 * cap + g]; }
+    __device__ __forceinline__ double gh(int g) const { return xywh[3 * cap + g]; }
+    __device__ __forceinline__ int glabel(int g) const { return label[g]; }
+    __device__ __forceinline__ unsigned char& taken(int t, int g) const { return flags[(size_t)t * cap + g]; }
+};
+
 // maskApi.c::bbIou on [x,y,w,h] in fp64
-__device__ __forceinline__ double bb_iou(double dl, double dt, double dw, double dh, double da, const GtSmem& gs, int g) {
-    const double gl = gs.gx[g], gt_ = gs.gy[g], gw = gs.gw[g], gh = gs.gh[g];
+template <class GT>
+__device__ __forceinline__ double bb_iou(double dl, double dt, double dw, double dh, double da, const GT& gs, int g) {
+    const double gl = gs.gx(g), gt_ = gs.gy(g), gw = gs.gw(g), gh = gs.gh(g);
     const double iw = fmin(dl + dw, gl + gw) - fmax(dl, gl);
     const double ih = fmin(dt + dh, gt_ + gh) - fmax(dt, gt_);
     if (iw > 0 && ih > 0) {
@@ -869,7 +894,8 @@ __device__ __forceinline__ double bb_iou(double dl, double dt, double dw, double
 }
 
 // Greedy COCO matching of the kept detections of one image (block-wide).  `gs` must have been staged.
-__device__ void match_image(MatchSmem& ms, GtSmem& gs, int nk, int C, int ng, const kodb_match_out& mo, int b, int max_det) {
+template <class GT>
+__device__ void match_image(MatchSmem& ms, const GT gs, int nk, int C, int ng, const kodb_match_out& mo, int b, int max_det) {
     const int tid = threadIdx.x;
     double thr_min = 1.0;
 #pragma unroll
@@ -886,7 +912,7 @@ __device__ void match_image(MatchSmem& ms, GtSmem& gs, int nk, int C, int ng, co
             const double dw = (double)ms.x2[d] - dl, dh = (double)ms.y2[d] - dt;
             const double da = dw * dh;
             for (int g = 0; g < ng; ++g)
-                if (gs.glabel[g] == c && bb_iou(dl, dt, dw, dh, da, gs, g) >= thr_min) mk |= 1ull << g;
+                if (gs.glabel(g) == c && bb_iou(dl, dt, dw, dh, da, gs, g) >= thr_min) mk |= 1ull << g;
         }
         ms.gmask[d] = mk;
     }
@@ -900,7 +926,7 @@ __device__ void match_image(MatchSmem& ms, GtSmem& gs, int nk, int C, int ng, co
     const double thr = fmin(mo.iou_thrs[t], 1.0 - 1e-10);
     for (int c = wid; c < C; c += nwarps) {
         bool has_gt = false;
-        for (int g = lane; g < ng; g += 32) has_gt |= (gs.glabel[g] == c);
+        for (int g = lane; g < ng; g += 32) has_gt |= (gs.glabel(g) == c);
         if (!__any_sync(KODB_FULL_MASK, has_gt)) continue;  // nothing to match: all detections of c are FP
         for (int d0 = 0; d0 < nk; d0 += 32) {
             const int dd = d0 + lane;
@@ -916,8 +942,8 @@ __device__ void match_image(MatchSmem& ms, GtSmem& gs, int nk, int C, int ng, co
                 double best = -1.0;
                 int m = -1;
                 for (int g = sub; g < ng; g += 8) {
-                    if (small ? !((mk >> g) & 1ull) : (gs.glabel[g] != c)) continue;
-                    if (gs.taken[t][g]) continue;
+                    if (small ? !((mk >> g) & 1ull) : (gs.glabel(g) != c)) continue;
+                    if (gs.taken(t, g)) continue;
                     const double iou = bb_iou(dl, dt, dw, dh, da, gs, g);
                     if (iou < thr || iou < best) continue;
                     best = iou;  // ascending g inside a slice: a later equal IoU replaces the earlier one
@@ -931,7 +957,7 @@ __device__ void match_image(MatchSmem& ms, GtSmem& gs, int nk, int C, int ng, co
                     if (ob > best || (ob == best && om > m)) { best = ob; m = om; }
                 }
                 if (m >= 0 && sub == 0) {
-                    gs.taken[t][m] = 1;
+                    gs.taken(t, m) = 1;
                     atomicOr(&ms.tp[d], 1 << t);
                 }
                 __syncwarp();
@@ -1757,7 +1783,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) select_nms_kernel(const __grid
             ms.score[tid] = rs; ms.cls[tid] = rc;
         }
         __syncthreads();
-        match_image(ms, gs, nk, C, gt_n, p.m, b, max_det);
+        match_image(ms, GtInSmem{gs}, nk, C, gt_n, p.m, b, max_det);
     }
     KODB_TRACE(8);
     if (p.trace && tid == 0) {
@@ -1784,7 +1810,70 @@ match_kernel(const float* __restrict__ dets, const int32_t* __restrict__ counts,
         ms.score[tid] = d[4]; ms.cls[tid] = (int)d[5];
     }
     __syncthreads();
+    match_image(ms, GtInSmem{gs}, nk, C, ng, mo, b, max_det);
+}
+
+// Crowded images (more than GT_CAP ground-truth boxes in one image): the same matching with the ground truth staged in a
+// global scratch instead of shared memory -- slower (L2 round trips in the greedy loop), no limit.  One CTA per image.
+__global__ void __launch_bounds__(NMS_THREADS, 1)
+match_crowded_kernel(const float* __restrict__ dets, const int32_t* __restrict__ counts, int C, int max_det, const void* gt_boxes,
+                     const int64_t* gt_labels, const int32_t* gt_offsets, int gt_dtype, const __grid_constant__ kodb_match_out mo,
+                     unsigned char* scratch, size_t per_image, int cap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MatchSmem& ms = *reinterpret_cast<MatchSmem*>(smem_raw);
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int nk = min(counts[b], max_det);
+    const int g0 = gt_offsets[b], ng = gt_offsets[b + 1] - g0;
+    unsigned char* base = scratch + (size_t)b * per_image;
+    GtInGlobal gs;
+    gs.xywh = reinterpret_cast<double*>(base);
+    gs.label = reinterpret_cast<int*>(base + (size_t)4 * cap * sizeof(double));
+    gs.flags = base + (size_t)4 * cap * sizeof(double) + (size_t)cap * sizeof(int);
+    gs.cap = cap;
+    for (int i = tid; i < KODB_NUM_IOU_THRS * cap; i += blockDim.x) gs.flags[i] = 0;
+    for (int g = tid; g < ng; g += blockDim.x) {
+        const long long lab = gt_labels[g0 + g];
+        if (lab >= 0 && lab < C) atomicAdd(reinterpret_cast<unsigned long long*>(mo.gt_count) + lab, 1ull);
+        double l, t, r, bt;
+        load_gt_xyxy(gt_boxes, gt_dtype, g0 + g, l, t, r, bt);
+        gs.xywh[g] = l; gs.xywh[cap + g] = t; gs.xywh[2 * cap + g] = r - l; gs.xywh[3 * cap + g] = bt - t;  // [l, t, r-l, b-t]
+        gs.label[g] = (int)lab;
+    }
+    if (tid < nk) {
+        const float* d = dets + ((int64_t)b * max_det + tid) * 6;
+        ms.x1[tid] = d[0]; ms.y1[tid] = d[1]; ms.x2[tid] = d[2]; ms.y2[tid] = d[3];
+        ms.score[tid] = d[4]; ms.cls[tid] = (int)d[5];
+    }
+    __threadfence_block();
+    __syncthreads();
     match_image(ms, gs, nk, C, ng, mo, b, max_det);
+}
+
+// stream-ordered scratch for the crowded path (rare: allocated per call, freed behind the kernel)
+static int launch_match_crowded(const float* dets, const int32_t* counts, int batch, int max_det, int C, const kodb_targets* gt,
+                                const kodb_match_out* m, cudaStream_t st) {
+    const int cap = (gt->max_per_image + 7) / 8 * 8;
+    const size_t per_image = ((size_t)cap * (4 * sizeof(double) + sizeof(int) + KODB_NUM_IOU_THRS) + 15) & ~(size_t)15;
+    void* scratch = nullptr;
+    if (cudaMallocAsync(&scratch, per_image * batch, st) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return KODB_ERR_CAPACITY;
+    }
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        if (cudaFuncSetAttribute(match_crowded_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMatchRegion) != cudaSuccess) {
+            cudaFreeAsync(scratch, st);
+            return KODB_ERR_LAUNCH;
+        }
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    match_crowded_kernel<<<batch, NMS_THREADS, kMatchRegion, st>>>(dets, counts, C, max_det, gt->boxes, gt->labels, gt->img_offsets,
+                                                                   gt->boxes_dtype, *m, (unsigned char*)scratch, per_image, cap);
+    const cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(scratch, st);
+    return e == cudaSuccess ? KODB_OK : KODB_ERR_LAUNCH;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1874,12 +1963,18 @@ static int check_common(const kodb_nms_cfg* cfg, const kodb_nms_out* out, int ba
     return KODB_OK;
 }
 
-static int setup_match(EvalParams& p, const kodb_targets* gt, const kodb_match_out* m) {
+// *crowded: an image has more ground-truth boxes than the select kernel stages in shared memory; the matching then runs
+// as its own launch behind the select kernel (match_crowded_kernel) instead of inside it
+static int setup_match(EvalParams& p, const kodb_targets* gt, const kodb_match_out* m, bool* crowded) {
     p.do_match = 0;
+    *crowded = false;
     if (!gt) return KODB_OK;
     if (!m || !m->rec_score || !m->rec_cls || !m->rec_tp || !m->gt_count) return KODB_ERR_INVALID_ARGUMENT;
     if (gt->batch != p.B) return KODB_ERR_INVALID_ARGUMENT;
-    if (gt->max_per_image > GT_CAP) return KODB_ERR_CAPACITY;
+    if (gt->max_per_image > GT_CAP) {
+        *crowded = true;
+        return KODB_OK;
+    }
     p.do_match = 1;
     p.gt_boxes = gt->boxes;
     p.gt_labels = gt->labels;
@@ -1986,7 +2081,8 @@ extern "C" int kodb_eval_tail(const kodb_head_level* heads_h, const kodb_level_c
     p.l2_stream = g_l2_stream;
     if (p.chunks_per_image > CHUNK_CAP) return KODB_ERR_UNSUPPORTED;
     if ((rc = carve_ws(p, workspace, workspace_bytes)) != KODB_OK) return rc;
-    if ((rc = setup_match(p, gt_h, match_h)) != KODB_OK) return rc;
+    bool crowded = false;
+    if ((rc = setup_match(p, gt_h, match_h, &crowded)) != KODB_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int stages = cfg_h->stage_mask ? cfg_h->stage_mask : 3;
     if (stages & 1) {
@@ -2002,7 +2098,9 @@ extern "C" int kodb_eval_tail(const kodb_head_level* heads_h, const kodb_level_c
             KODB_CHECK_LAUNCH();
         }
     }
-    return (stages & 2) ? launch_select(p, st) : KODB_OK;
+    if (!(stages & 2)) return KODB_OK;
+    if ((rc = launch_select(p, st)) != KODB_OK || !crowded) return rc;
+    return launch_match_crowded(p.out.dets, p.out.counts, p.B, p.cfg.max_det, p.C, gt_h, match_h, st);
 }
 
 extern "C" int kodb_nms(const float* detections, int32_t batch, int64_t rows, const kodb_nms_cfg* cfg_h,
@@ -2035,14 +2133,17 @@ extern "C" int kodb_nms(const float* detections, int32_t batch, int64_t rows, co
     p.l2_stream = 0;
     if (p.chunks_per_image > CHUNK_CAP) return KODB_ERR_UNSUPPORTED;
     if ((rc = carve_ws(p, workspace, workspace_bytes)) != KODB_OK) return rc;
-    if ((rc = setup_match(p, gt_h, match_h)) != KODB_OK) return rc;
+    bool crowded = false;
+    if ((rc = setup_match(p, gt_h, match_h, &crowded)) != KODB_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int stages = cfg_h->stage_mask ? cfg_h->stage_mask : 3;
     if (stages & 1) {
         cand_kernel<false, 1><<<dim3(p.tiles_per_image, batch), CAND_THREADS, 0, st>>>(p);
         KODB_CHECK_LAUNCH();
     }
-    return (stages & 2) ? launch_select(p, st) : KODB_OK;
+    if (!(stages & 2)) return KODB_OK;
+    if ((rc = launch_select(p, st)) != KODB_OK || !crowded) return rc;
+    return launch_match_crowded(p.out.dets, p.out.counts, p.B, p.cfg.max_det, p.C, gt_h, match_h, st);
 }
 
 extern "C" int kodb_map_match(const float* dets, const int32_t* counts, int32_t batch, int32_t max_det,
@@ -2052,7 +2153,8 @@ extern "C" int kodb_map_match(const float* dets, const int32_t* counts, int32_t 
         num_classes > KODB_MAX_CLASSES)
         return KODB_ERR_INVALID_ARGUMENT;
     if (gt_h->batch != batch) return KODB_ERR_INVALID_ARGUMENT;
-    if (gt_h->max_per_image > GT_CAP) return KODB_ERR_CAPACITY;
+    if (gt_h->max_per_image > GT_CAP)
+        return launch_match_crowded(dets, counts, batch, max_det, num_classes, gt_h, match_h, (cudaStream_t)stream);
     static bool attr_set[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);

@@ -369,6 +369,41 @@ def test_matching_and_ap(B, S, C, dtype, oracle_lib):
     assert abs(got2["avg_mAP"] - want["avg_mAP"]) < 1e-4
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_matching_crowded_image(dtype, oracle_lib):
+    """One image with more ground-truth boxes than the select kernel stages in shared memory (512): the matching runs
+    as its own launch with the ground truth in a global scratch -- no capacity error, same TP bits (fused eval tail and
+    the standalone kodb_map_match)."""
+    B, S, C = 3, 640, 10
+    heads = syn.make_head(B, S, C, seed=77)
+    targets = syn.make_targets(B, S, C, seed=9, n_min=2, n_max=12, dtype=dtype)
+    g = torch.Generator().manual_seed(4)
+    n_big = 700
+    xy = torch.rand(n_big, 2, generator=g, dtype=torch.float64) * (S - 80)
+    wh = 8 + torch.rand(n_big, 2, generator=g, dtype=torch.float64) * 64
+    big_boxes = torch.cat([xy, xy + wh], 1).to(dtype)
+    big_labels = torch.randint(0, C, (n_big,), generator=g)
+    targets = list(targets)
+    targets[1] = (big_boxes, big_labels)
+    syn.inject_ground_truth(heads, targets, S, fraction=0.5)
+    ev = DeviceCocoMapEvaluator(C, device=DEV)
+    res, rec = N.eval_tail(FeatureShape(S, S), _to_dev(heads), default_anchor_info(), 0.001, 0.6, targets=targets,
+                           gt_count=ev.gt_count)
+    counts = res.counts.cpu().numpy()
+    dets = res.dets.cpu().numpy()
+    ms, _ = _match_oracle([dets[b, :counts[b]] for b in range(B)], targets, C)
+    tp = rec.tp.cpu().numpy()
+    for b, m in enumerate(ms):
+        bits = (m.tp * (1 << np.arange(4))[None, :]).sum(1).astype(np.uint8)
+        assert np.array_equal(tp[b, :counts[b]], bits), b
+    assert int(ms[1].tp[:, 1].sum()) > 0, "the crowded image must hold true positives"
+    assert ev.gt_count.cpu().numpy().tolist() == np.sum([m.gt_count for m in ms], 0).tolist()
+    ev2 = DeviceCocoMapEvaluator(C, device=DEV)
+    ev2.add_detections(res.dets, res.counts, targets)  # kodb_map_match
+    assert torch.equal(ev2._records[0].tp, rec.tp)
+    assert torch.equal(ev2.gt_count, ev.gt_count)
+
+
 def test_coco_rule_kats_gpu():
     """The hand-derived pycocotools known answers (tests/_coco_kats.py) through the CUDA matching + AP kernels, fed
     the way the reference's callback feeds its evaluator (python lists, pycoco_map_eval.py:66-106)."""
