@@ -184,8 +184,9 @@ typedef struct kodb_head_conv_level {
 /* kodb_head_forward: Yolov5Head.forward (kod/nn/heads/yolov5.py:170-178) of up to three pyramid levels in one launch:
  * per level the box / objectness / class 1x1 convolutions as ONE tf32 tensor-core GEMM that reads the feature map once
  * and writes the three planar tensors.  fp32 in, tf32 multiply, fp32 accumulate + bias (the precision class of torch's
- * default convolution policy, torch.backends.cudnn.allow_tf32).  in_channels % 32 == 0, H*W % 4 == 0,
- * A*(5+C) <= 256; KODB_ERR_UNSUPPORTED otherwise (callers fall back to the three separate convolutions themselves). */
+ * default convolution policy, torch.backends.cudnn.allow_tf32).  A level with in_channels % 32 != 0, H*W % 4 != 0 (the
+ * 13x13 grid of a 416 input), A*(5+C) > 256 or a base address that is not 16-byte aligned runs on a plain SIMT kernel
+ * (fp32 multiply-add) inside the same call -- slower per byte, but those levels are small. */
 int kodb_head_forward(const kodb_head_conv_level* levels_h /* [num_levels], 1..3 */, int32_t num_levels, int32_t batch,
                       int32_t num_anchors, int32_t num_classes, void* stream);
 

@@ -336,6 +336,60 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_forward_kernel(const __gri
     }
 }
 
+// =========================================================================================================
+// Levels the TMA / tcgen05 path does not take (H*W not a multiple of 4 -- the 13x13 level of a 416 input --, in_channels
+// not a multiple of 32, more than 256 output channels, misaligned tensors): a plain SIMT kernel, thread = cell, 16 output
+// channels per pass with their weight rows staged in shared memory, fp32 multiply-add (exact fp32, no tf32 rounding).
+// These levels are small; the kernel only has to be correct and coalesced.
+constexpr int HG_THREADS = 128;
+constexpr int HG_NCH = 16;     // output channels per pass
+constexpr int HG_KCH = 128;    // input channels staged per round (HG_NCH * HG_KCH floats = 8 KB)
+
+struct HeadGenericParams {
+    const float* x;
+    const float* w[3];     // (rows_i, K)
+    const float* bias[3];
+    float* out[3];
+    int rows[3];           // A*4, A, A*C
+    int K, HW;
+};
+
+__global__ void __launch_bounds__(HG_THREADS) head_generic_kernel(const __grid_constant__ HeadGenericParams p) {
+    __shared__ float sw[HG_NCH][HG_KCH];
+    const int b = blockIdx.y, cell = blockIdx.x * HG_THREADS + threadIdx.x;
+    const bool live = cell < p.HW;
+    const float* xb = p.x + (size_t)b * p.K * p.HW + (live ? cell : 0);
+    for (int ti = 0; ti < 3; ++ti) {
+        for (int n0 = 0; n0 < p.rows[ti]; n0 += HG_NCH) {
+            const int nn = min(HG_NCH, p.rows[ti] - n0);
+            float acc[HG_NCH];
+#pragma unroll
+            for (int u = 0; u < HG_NCH; ++u) acc[u] = 0.0f;
+            for (int k0 = 0; k0 < p.K; k0 += HG_KCH) {
+                const int kk = min(HG_KCH, p.K - k0);
+                __syncthreads();  // the previous round's readers are done
+                for (int i = threadIdx.x; i < HG_NCH * HG_KCH; i += HG_THREADS) {
+                    const int u = i / HG_KCH, k = i - u * HG_KCH;
+                    sw[u][k] = (u < nn && k < kk) ? __ldg(p.w[ti] + (size_t)(n0 + u) * p.K + k0 + k) : 0.0f;
+                }
+                __syncthreads();
+                if (live) {
+                    for (int k = 0; k < kk; ++k) {
+                        const float xv = __ldg(xb + (size_t)(k0 + k) * p.HW);  // 32 lanes: 128 contiguous bytes
+#pragma unroll
+                        for (int u = 0; u < HG_NCH; ++u) acc[u] = fmaf(xv, sw[u][k], acc[u]);
+                    }
+                }
+            }
+            if (live) {
+#pragma unroll
+                for (int u = 0; u < HG_NCH; ++u)
+                    if (u < nn) p.out[ti][((size_t)b * p.rows[ti] + n0 + u) * p.HW + cell] = acc[u] + __ldg(p.bias[ti] + n0 + u);
+            }
+        }
+    }
+}
+
 // ---- host -----------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -365,9 +419,8 @@ extern "C" int kodb_head_forward(const kodb_head_conv_level* levels_h, int32_t n
         return KODB_ERR_INVALID_ARGUMENT;
     const int n3 = num_anchors * (5 + num_classes);
     const int n_pad = (n3 + 15) / 16 * 16;
-    if (n_pad > 256) return KODB_ERR_UNSUPPORTED;  // one UMMA tile in N (3 anchors: up to 80 classes)
     EncodeTiledFn encode = get_encoder();
-    if (!encode) return KODB_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
     HeadParams p;
     p.n_pad = n_pad;
     p.acc_cols = 32;
@@ -375,15 +428,34 @@ extern "C" int kodb_head_forward(const kodb_head_conv_level* levels_h, int32_t n
     p.b_stage_bytes = n_pad * 128;
     // A operand (MN-major tf32): the only legal shared-memory layout is the 128-byte swizzle with a 32-byte atom
     // (cutlass sm100_common.inl:92; UMMA layout type SWIZZLE_128B_BASE32B)
-    int tiles = 0;
-    for (int l = 0; l < num_levels; ++l) {
-        const kodb_head_conv_level& h = levels_h[l];
-        if (!h.x || !h.weight || !h.out_box || !h.out_obj || !h.out_cls || !h.bias_box || !h.bias_obj || !h.bias_cls)
+    int tiles = 0, n_tc = 0;
+    for (int li = 0; li < num_levels; ++li) {
+        const kodb_head_conv_level& h = levels_h[li];
+        if (!h.x || !h.weight || !h.out_box || !h.out_obj || !h.out_cls || !h.bias_box || !h.bias_obj || !h.bias_cls ||
+            h.in_channels < 1 || h.H < 1 || h.W < 1)
             return KODB_ERR_INVALID_ARGUMENT;
-        if (h.in_channels < HD_KB || h.in_channels % HD_KB || h.H < 1 || h.W < 1) return KODB_ERR_UNSUPPORTED;
         const int HW = h.H * h.W;
-        if (HW % 4) return KODB_ERR_UNSUPPORTED;  // TMA: strides are multiples of 16 bytes
-        if ((reinterpret_cast<uintptr_t>(h.x) | reinterpret_cast<uintptr_t>(h.weight)) & 15u) return KODB_ERR_INVALID_ARGUMENT;
+        // the tensor-core path needs: 32-channel k-blocks, 16-byte global strides for the TMA (H*W % 4), 16-byte aligned
+        // bases, one UMMA tile in N (A*(5+C) <= 256: three anchors up to 80 classes)
+        const bool tc = encode && n_pad <= 256 && h.in_channels % HD_KB == 0 && HW % 4 == 0 &&
+                        !((reinterpret_cast<uintptr_t>(h.x) | reinterpret_cast<uintptr_t>(h.weight)) & 15u);
+        if (!tc) {  // small / odd level: the SIMT kernel
+            HeadGenericParams g;
+            g.x = h.x;
+            g.K = h.in_channels;
+            g.HW = HW;
+            g.rows[0] = num_anchors * 4; g.rows[1] = num_anchors; g.rows[2] = num_anchors * num_classes;
+            g.w[0] = h.weight;
+            g.w[1] = g.w[0] + (size_t)g.rows[0] * g.K;
+            g.w[2] = g.w[1] + (size_t)g.rows[1] * g.K;
+            g.bias[0] = h.bias_box; g.bias[1] = h.bias_obj; g.bias[2] = h.bias_cls;
+            g.out[0] = h.out_box; g.out[1] = h.out_obj; g.out[2] = h.out_cls;
+            if (batch > 65535) return KODB_ERR_UNSUPPORTED;
+            head_generic_kernel<<<dim3((HW + HG_THREADS - 1) / HG_THREADS, batch), HG_THREADS, 0, st>>>(g);
+            KODB_CHECK_LAUNCH();
+            continue;
+        }
+        const int l = n_tc++;
         HeadLevelParams& L = p.lv[l];
         L.K = h.in_channels;
         L.HW = HW;
@@ -418,7 +490,8 @@ extern "C" int kodb_head_forward(const kodb_head_conv_level* levels_h, int32_t n
                 return KODB_ERR_INVALID_ARGUMENT;
         }
     }
-    for (int l = num_levels; l < KODB_NUM_LEVELS; ++l) {  // absent levels own no tiles
+    if (n_tc == 0) return KODB_OK;
+    for (int l = n_tc; l < KODB_NUM_LEVELS; ++l) {  // absent levels own no tiles
         p.lv[l] = HeadLevelParams{};
         p.tma_x[l] = p.tma_x[0];
         p.tma_w[l] = p.tma_w[0];
@@ -460,7 +533,7 @@ extern "C" int kodb_head_forward(const kodb_head_conv_level* levels_h, int32_t n
     const int per_sm = smem <= 110 * 1024 ? 2 : 1;
     int grid = sms[dev] * per_sm;
     if (grid > units) grid = units;
-    head_forward_kernel<<<grid, HD_THREADS, smem, (cudaStream_t)stream>>>(p);
+    head_forward_kernel<<<grid, HD_THREADS, smem, st>>>(p);
     KODB_CHECK_LAUNCH();
     return KODB_OK;
 }

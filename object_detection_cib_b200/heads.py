@@ -10,8 +10,9 @@ once and writes the three planar `[B][A*P][H][W]` tensors the detection tail con
 * Backward: dX / dW / db with library GEMMs (cuBLAS through torch) – the gradients of the planar tensors come straight
   from the train tail, already in the layout the GEMMs want.
 Precision: fp32 in, tf32 multiply, fp32 accumulate, i.e. what torch's default convolution policy
-(`torch.backends.cudnn.allow_tf32 = True`) computes on this GPU.  Shapes the kernel does not take (in_channels % 32,
-H*W % 4, A*(5+C) > 256) raise – there is no silent fallback.
+(`torch.backends.cudnn.allow_tf32 = True`) computes on this GPU.  Levels outside the tensor-core path (in_channels % 32,
+H*W % 4 – the 13x13 grid of a 416 input –, A*(5+C) > 256) run on a SIMT kernel of the same library in fp32; there is no
+torch / cuDNN fallback.
 """
 from __future__ import annotations
 
