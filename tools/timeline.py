@@ -41,7 +41,7 @@ torch.cuda._sleep(int(0.08 * 1.9e9))  # the host queues everything behind this
 base.record(main)
 for s in branches + sides:
     s.wait_stream(main)
-for i in range(steps):
+for i in range(steps if "P" not in kinds else 0):
     st = wl.sets[i % ns]
     br, sd = branches[i % ns], sides[i % ns]
     with torch.cuda.stream(br):
@@ -62,6 +62,30 @@ for i in range(steps):
             e0.record(sd); wl.train_call(st); e1.record(sd)
             rec.append((i, "train", e0, e1))
         br.wait_stream(sd)
+if "P" in kinds:
+    # phased schedule: the candidate kernels of `ns` steps together, then their select/NMS kernels and train tails together
+    rec = []
+    for g0 in range(0, steps, ns):
+        for i in range(g0, min(g0 + ns, steps)):
+            with torch.cuda.stream(branches[i % ns]):
+                wl.eval_call(wl.sets[i % ns], 1)
+        join = [E() for _ in range(ns)]
+        for k in range(ns):
+            join[k].record(branches[k])
+        for s in branches + sides:
+            for k in range(ns):
+                s.wait_event(join[k])
+        for i in range(g0, min(g0 + ns, steps)):
+            with torch.cuda.stream(branches[i % ns]):
+                wl.eval_call(wl.sets[i % ns], 2)
+            with torch.cuda.stream(sides[i % ns]):
+                wl.train_call(wl.sets[i % ns])
+        join2 = [E() for _ in range(2 * ns)]
+        for k, s in enumerate(branches + sides):
+            join2[k].record(s)
+        for s in branches + sides:
+            for k in range(2 * ns):
+                s.wait_event(join2[k])
 for s in branches + sides:
     main.wait_stream(s)
 end = E()
