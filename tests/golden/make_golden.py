@@ -515,7 +515,9 @@ def head_cases():
     out = {}
     B, C, A = 2, 10, 3
     g = torch.Generator().manual_seed(91)
-    cfgs = [(64, 16, 16, 8), (128, 12, 12, 16), (256, 6, 6, 32)]  # (in_channels, H, W, stride); 6x6 = 36 cells: ragged tile
+    # (in_channels, H, W, stride); 6x6 = 36 cells: ragged tile; 13x13 (the hl level of the reference's default 416 input)
+    # and 48 channels: outside the tensor-core path (SIMT kernel)
+    cfgs = [(64, 16, 16, 8), (128, 12, 12, 16), (256, 6, 6, 32), (128, 13, 13, 32), (48, 10, 7, 8)]
     out["meta"] = np.array([B, C, A], np.int64)
     out["cfgs"] = np.array(cfgs, np.int64)
     for l, (K, Hh, Ww, stride) in enumerate(cfgs):
