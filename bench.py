@@ -36,7 +36,9 @@ sys.path.insert(0, ROOT)
 
 METRIC = "yolov5s_tail_images_per_s"
 UNIT = "images/s"
-SPLIT_CHAINS = os.environ.get("KODB_BENCH_SPLIT", "0") == "1"
+# the train tails and the eval tails of the K steps as independent chains of the graph (they share inputs, not results):
+# 1.5 us per step better than joining them at every step (tools/exp_sets.sh); KODB_BENCH_SPLIT=0 restores the joined form
+SPLIT_CHAINS = os.environ.get("KODB_BENCH_SPLIT", "1") == "1"
 NSETS = int(os.environ.get("KODB_BENCH_NSETS", "3"))  # rotating input sets: 3 x (96.8 MB head + 96.8 MB grads) >> 126 MB L2
 
 
@@ -255,9 +257,10 @@ class TailWorkload:
 
 def capture_steps(wl, n_steps, mode, dev):
     """ONE CUDA graph holding `n_steps` consecutive steps.
-      "pipelined": the steps of input set s run on branch s (each with its own side stream for the train tail), so up to
-                   NSETS independent steps are in flight and the latency-bound select/NMS kernel of one step overlaps the
-                   streaming kernels of the next;
+      "pipelined": the steps of input set s run on branch s, so up to NSETS independent steps are in flight and the
+                   latency-bound select/NMS kernel of one step overlaps the streaming kernels of the next; by default
+                   (SPLIT_CHAINS) the eval tails (candidates -> select/NMS) and the train tails of a set form two independent
+                   chains, otherwise the train tail forks off behind the candidate kernel and joins before the set's next step;
       "step":      steps strictly one after the other; inside a step the train tail runs beside the select/NMS kernel
                    (both only read the head maps) -- what a loop that cannot overlap steps sees;
       "serial":    every kernel strictly after the previous one.
@@ -657,8 +660,10 @@ def run_ours(a):
                        "classes": Cn, "parallelism": f"dp{world} (shard by image, no data-path collective)",
                        "l2": f"inputs rotate over {NSETS} sets ({NSETS}x{(b_eval * B) / 1e6:.0f} MB head + grads) > 126 MB L2",
                        "launch": f"ONE cuda-graph launch holds all {a.steps} timed steps (device-bound timed region); per step: "
-                                 f"candidate kernel, then select/NMS kernel || train tail on two captured streams; consecutive "
-                                 f"steps pipelined over {NSETS} graph branches (one per input set)",
+                                 f"candidate kernel -> select/NMS kernel on an eval chain, train tail on a train chain; "
+                                 + ("the eval chain and the train chain of an input set run independently (they share inputs, not "
+                                    "results); " if SPLIT_CHAINS else "the chains of a step join before the next step of the set; ")
+                                 + f"consecutive steps pipelined over {NSETS} input sets (one pair of chains per set)",
                        "numa": numa},
             "gpu_launches": wl_launches(a.steps),
             "per_rank_ms_per_step": m["per_rank_ms_per_step"],

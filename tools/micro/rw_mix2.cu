@@ -86,6 +86,8 @@ int main() {
         report("st.cg", 296, [&](float4* p) { wr<2><<<296, 256, 0, s2>>>(p, n4); });
         report("st.wt", 296, [&](float4* p) { wr<3><<<296, 256, 0, s2>>>(p, n4); });
         for (int gw : {74, 148, 296}) report("tma-bulk", gw, [&](float4* p) { wr_bulk<<<gw, 128, 0, s2>>>(p, n4); });
+        report("memsetAsync", 0, [&](float4* p) { cudaMemsetAsync(p, 0, bytes, s2); });
+        report("memsetD32", 0, [&](float4* p) { cudaMemsetAsync(p, 0, bytes / 2, s2); cudaMemsetAsync((char*)p + bytes / 2, 0, bytes / 2, s2); });
     }
     return 0;
 }
