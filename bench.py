@@ -39,6 +39,10 @@ UNIT = "images/s"
 # the train tails and the eval tails of the K steps as independent chains of the graph (they share inputs, not results):
 # 1.5 us per step better than joining them at every step (tools/exp_sets.sh); KODB_BENCH_SPLIT=0 restores the joined form
 SPLIT_CHAINS = os.environ.get("KODB_BENCH_SPLIT", "1") == "1"
+# the select/NMS kernels (64 latency-bound CTAs) on streams of their own with the highest stream priority: their CTAs are
+# placed ahead of the pending CTAs of the streaming kernels (-0.6 us per step, tools/exp_selprio.sh); 0 = on the candidate
+# kernel's stream
+SEL_PRIO = int(os.environ.get("KODB_BENCH_SEL_PRIO", "-3"))
 NSETS = int(os.environ.get("KODB_BENCH_NSETS", "3"))  # rotating input sets: 3 x (96.8 MB head + 96.8 MB grads) >> 126 MB L2
 
 
@@ -271,20 +275,34 @@ def capture_steps(wl, n_steps, mode, dev):
     branches = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(ns)]
     sides = [torch.cuda.Stream(device=dev) for _ in range(ns)]
     evs = [torch.cuda.Event() for _ in range(ns)]
+    sels = [torch.cuda.Stream(device=dev, priority=SEL_PRIO) for _ in range(ns)] if SEL_PRIO else []
+    sel_evs = [torch.cuda.Event() for _ in range(ns)]
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g, stream=cap):
         if mode == "pipelined" and SPLIT_CHAINS and wl.train and wl.evalt:
             # the train tails and the eval tails of the K steps as independent chains (they share inputs, not results)
             cur = torch.cuda.current_stream(dev)
-            for b in branches + sides:
+            for b in branches + sides + sels:
                 b.wait_stream(cur)
             for i in range(n_steps):
                 st = wl.sets[i % ns]
-                with torch.cuda.stream(branches[i % ns]):
-                    wl.eval_call(st)
+                if SEL_PRIO:
+                    # the select/NMS kernel on a stream of its own with a higher priority than the candidate kernel
+                    with torch.cuda.stream(branches[i % ns]):
+                        if i >= ns:
+                            branches[i % ns].wait_event(sel_evs[i % ns])  # the set's previous select kernel (workspace reuse)
+                        wl.eval_call(st, 1)
+                        evs[i % ns].record(branches[i % ns])
+                    with torch.cuda.stream(sels[i % ns]):
+                        sels[i % ns].wait_event(evs[i % ns])
+                        wl.eval_call(st, 2)
+                        sel_evs[i % ns].record(sels[i % ns])
+                else:
+                    with torch.cuda.stream(branches[i % ns]):
+                        wl.eval_call(st)
                 with torch.cuda.stream(sides[i % ns]):
                     wl.train_call(st)
-            for b in branches + sides:
+            for b in branches + sides + sels:
                 cur.wait_stream(b)
         elif mode == "pipelined":
             cur = torch.cuda.current_stream(dev)
@@ -301,7 +319,7 @@ def capture_steps(wl, n_steps, mode, dev):
         else:
             for i in range(n_steps):
                 wl.step_serial(i)
-    return g, (cap, branches, sides, evs)
+    return g, (cap, branches, sides, evs, sels, sel_evs)
 
 
 def measure_workload(wl, steps, warmup, env, full=True):
@@ -660,7 +678,8 @@ def run_ours(a):
                        "classes": Cn, "parallelism": f"dp{world} (shard by image, no data-path collective)",
                        "l2": f"inputs rotate over {NSETS} sets ({NSETS}x{(b_eval * B) / 1e6:.0f} MB head + grads) > 126 MB L2",
                        "launch": f"ONE cuda-graph launch holds all {a.steps} timed steps (device-bound timed region); per step: "
-                                 f"candidate kernel -> select/NMS kernel on an eval chain, train tail on a train chain; "
+                                 f"candidate kernel -> select/NMS kernel (stream priorities -1 / {SEL_PRIO if SEL_PRIO else -1}) on an eval chain, "
+                                 f"train tail (priority 0) on a train chain; "
                                  + ("the eval chain and the train chain of an input set run independently (they share inputs, not "
                                     "results); " if SPLIT_CHAINS else "the chains of a step join before the next step of the set; ")
                                  + f"consecutive steps pipelined over {NSETS} input sets (one pair of chains per set)",
