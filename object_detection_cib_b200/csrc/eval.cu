@@ -30,6 +30,7 @@
 #include <stdlib.h>
 
 #include "kodb_common.cuh"
+#include "tma_common.cuh"
 
 namespace kodb {
 
@@ -78,6 +79,10 @@ struct EvalParams {
     int ns, sample_stride;     // sample tiles per image: tiles 0, S, 2S, ... (one per warp of the image's sample CTA)
     unsigned magic_b, magic_s1; // ceil(2^32 / B), ceil(2^32 / (S - 1)) when exact over the grid's index range, else 0
     int hot_target;            // estimated number of listed candidates per image the floor aims at
+    // tile loads by TMA (flat planar head tensors): per level (cell, plane, image) maps of the objectness and class logits,
+    // boxes of 128 cells x 1 plane / 128 cells x NQ planes; 0: per-lane cp.async copies (any strides)
+    int use_tma;
+    CUtensorMap tma_obj[KODB_NUM_LEVELS], tma_cls[KODB_NUM_LEVELS];
     int l2_stream;             // class planes are loaded with the L2 evict-first policy (tuning knob KODB_EVAL_L2_STREAM)
     int floor_polls;           // bounded wait (x100 ns) for the floor at a tile's second chance; 0 in production (no gain
                                // measured on B200), large in the tests that must exercise floors on small batches
@@ -416,9 +421,12 @@ __device__ __forceinline__ unsigned fix_borderline(unsigned cmv, unsigned border
 
 template <int NQ>
 __global__ void __launch_bounds__(CW_WARPS * 32, 6) cand_floor_kernel(const __grid_constant__ EvalParams p) {
-    extern __shared__ __align__(16) unsigned char cw_smem_raw[];
+    extern __shared__ __align__(128) unsigned char cw_smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    CandWarpSmem<NQ>& sm = reinterpret_cast<CandWarpSmem<NQ>*>(cw_smem_raw)[wid];
+    // (128-byte alignment of the stashes: destination of the TMA tile loads)
+    unsigned char* cw_smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(cw_smem_raw) + 127) & ~(uintptr_t)127);
+    CandWarpSmem<NQ>& sm = reinterpret_cast<CandWarpSmem<NQ>*>(cw_smem)[wid];
+    __shared__ __align__(8) uint64_t s_tile_bar[CW_WARPS];  // one mbarrier per warp: arrival of the warp's tile (TMA path)
     // work order: CTA b < B is image b's sample CTA (one sample tile per warp, tiles 0, S, 2S, ...; it runs first and
     // keeps the sample histogram in shared memory); the other CTAs take the remaining tiles, image index fastest, so
     // that neighbouring warps work on different images and the per-image atomics do not pile up on one address
@@ -459,14 +467,28 @@ __global__ void __launch_bounds__(CW_WARPS * 32, 6) cand_floor_kernel(const __gr
     const bool in_range = cell0 < ncell;  // tiles are multiples of 4 cells
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     constexpr unsigned CELL_MASK = (1u << NQ) - 1u;  // the NQ class bits of one cell
-    // Asynchronous 16-byte copies global -> the warp's shared stash (LDGSTS): all of the tile's bytes are in flight
-    // at once without holding registers, so three CTAs fit on an SM.  The obj logits land in sm.o and are replaced
-    // by their sigmoid below.
     const unsigned sq0 = (unsigned)__cvta_generic_to_shared(&sm.q[0][cell0]);  // class u of the stash: + u * 512 bytes
     const unsigned long long l2pol = l2_evict_first_policy(p.l2_stream != 0);
-    if (in_range) cp_async16(&sm.o[cell0], obj_base + cell0);  // (normal policy: the loss reads the obj planes too)
-    else *reinterpret_cast<float4*>(&sm.o[cell0]) = zero4;
-    {
+    const bool tma = p.use_tma != 0;
+    uint64_t* tbar = &s_tile_bar[wid];
+    if (tma) {
+        // TMA: ONE bulk tensor copy brings the tile's objectness logits (128 cells x 1 plane) and one its class logits
+        // (128 cells x NQ planes) into the warp's stash -- no per-lane addresses, no per-plane copy instructions; cells
+        // beyond the plane and planes beyond the last anchor's arrive as zeros.  The class planes are read once (L2
+        // evict-first); the objectness plane is read by the loss too (normal policy).
+        if (lane == 0) {
+            mbar_init(tbar, 1);
+            mbar_fence_init();
+            mbar_expect_tx(tbar, (uint32_t)((NQ + 1) * WT_CELLS * sizeof(float)));
+            tma_load_3d(&sm.o[0], &p.tma_obj[L], tbar, c0, a, b);
+            tma_load_3d_hint(&sm.q[0][0], &p.tma_cls[L], tbar, c0, a * C, b, l2pol);
+        }
+        __syncwarp();
+    } else {
+        // Asynchronous 16-byte copies global -> the warp's shared stash (LDGSTS): all of the tile's bytes are in flight
+        // at once without holding registers.  The obj logits land in sm.o and are replaced by their sigmoid below.
+        if (in_range) cp_async16(&sm.o[cell0], obj_base + cell0);  // (normal policy: the loss reads the obj planes too)
+        else *reinterpret_cast<float4*>(&sm.o[cell0]) = zero4;
         const int nld = in_range ? min(C, CGROUP) : 0;
         const float* cp = cls_base + cell0;
         if (nld == NQ) {  // the usual case: every class slot of the group is real -- no per-copy predicate
@@ -480,8 +502,8 @@ __global__ void __launch_bounds__(CW_WARPS * 32, 6) cand_floor_kernel(const __gr
                 cp += cls_step;
             }
         }
+        cp_async_commit();
     }
-    cp_async_commit();
     // the image's floor, if its sample CTA is through already (the read overlaps the copies above)
     int floor_bin = HB - 1;  // HB - 1: list everything
     if (!sample) {
@@ -507,7 +529,13 @@ __global__ void __launch_bounds__(CW_WARPS * 32, 6) cand_floor_kernel(const __gr
             if (richc && !fastf) forcef |= 1u << v;
         }
     };
-    cp_async_wait_all();  // every lane reads back only what it copied itself until the __syncwarp further down
+    unsigned tile_phase = 0;
+    if (tma) {
+        mbar_wait(tbar, tile_phase);  // (acquire: the async-proxy writes of the copy are visible to every lane)
+        tile_phase ^= 1u;
+    } else {
+        cp_async_wait_all();  // every lane reads back only what it copied itself until the __syncwarp further down
+    }
     {
         const float4 xo = *reinterpret_cast<const float4*>(&sm.o[cell0]);
         const float x[4] = {xo.x, xo.y, xo.z, xo.w};
@@ -538,16 +566,26 @@ __global__ void __launch_bounds__(CW_WARPS * 32, 6) cand_floor_kernel(const __gr
         const int j0 = grp * CGROUP, jn = min(C - j0, CGROUP);
         if (grp > 0) {
             __syncwarp();  // the previous group's readers of the stash are done
-            const float* cp = cls_base + (int64_t)j0 * cls_step + cell0;
-            const int nld = in_range ? jn : 0;
+            if (tma) {
+                if (lane == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy reads before the async-proxy overwrite
+                    mbar_expect_tx(tbar, (uint32_t)(NQ * WT_CELLS * sizeof(float)));
+                    tma_load_3d_hint(&sm.q[0][0], &p.tma_cls[L], tbar, c0, a * C + j0, b, l2pol);
+                }
+                mbar_wait(tbar, tile_phase);
+                tile_phase ^= 1u;
+            } else {
+                const float* cp = cls_base + (int64_t)j0 * cls_step + cell0;
+                const int nld = in_range ? jn : 0;
 #pragma unroll
-            for (int u = 0; u < NQ; ++u) {
-                if (u < nld) cp_async16_s_ef(sq0 + u * (WT_CELLS * 4), cp, l2pol);
-                else *reinterpret_cast<float4*>(&sm.q[u][cell0]) = zero4;
-                cp += cls_step;
+                for (int u = 0; u < NQ; ++u) {
+                    if (u < nld) cp_async16_s_ef(sq0 + u * (WT_CELLS * 4), cp, l2pol);
+                    else *reinterpret_cast<float4*>(&sm.q[u][cell0]) = zero4;
+                    cp += cls_step;
+                }
+                cp_async_commit();
+                cp_async_wait_all();
             }
-            cp_async_commit();
-            cp_async_wait_all();
         }
         // pair (u, v): the sign bit of (tau[v] - q[u][v]) is funnel-shifted into one mask per cell (four
         // independent dependency chains); class u ends at bit NQ-1-u of the chain.  Same for the floor test.
@@ -752,7 +790,7 @@ __global__ void __launch_bounds__(CW_WARPS * 32, 6) cand_floor_kernel(const __gr
 
 template <int NQ>
 static int launch_cand_warp(const EvalParams& p, dim3 grid, cudaStream_t st) {
-    const size_t smem = sizeof(CandWarpSmem<NQ>) * CW_WARPS;
+    const size_t smem = sizeof(CandWarpSmem<NQ>) * CW_WARPS + 128;  // (+ alignment of the stashes)
     static bool attr_set[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -2033,6 +2071,46 @@ extern "C" int kodb_debug_take_completions(void) {
 extern "C" void kodb_debug_set_floor_polls(int n) { kodb::g_floor_polls = n > 0 ? n : 0; }
 extern "C" void kodb_debug_set_hot_target(int n) { kodb::g_hot_target = n > 0 ? n : kodb::HOT_TARGET; }
 
+// Tensor maps for the candidate kernel's tile loads: possible when every level's objectness and class tensors are flat planar
+// arrays [B][A][P][H*W] (the Detect head's own layout); anything else keeps the per-lane cp.async copies.
+static void setup_cand_tma(kodb::EvalParams& p, int nq) {
+    using namespace kodb;
+    p.use_tma = 0;
+    static int knob = -1;
+    if (knob < 0) {
+        const char* e = getenv("KODB_EVAL_TMA");
+        knob = e ? (atoi(e) != 0) : 1;
+    }
+    EncodeTiledFn encode = knob ? tensormap_encoder() : nullptr;
+    if (!encode) return;
+    for (int l = 0; l < KODB_NUM_LEVELS; ++l) {
+        const kodb_head_level& h = p.g.head[l];
+        const int64_t HW = (int64_t)p.g.lv[l].H * p.g.lv[l].W, A = p.g.lv[l].num_anchors, C = p.C;
+        if (HW % 4 || h.obj_sa != HW || h.obj_sb != A * HW || h.cls_sp != HW || h.cls_sa != C * HW || h.cls_sb != A * C * HW) return;
+        if ((reinterpret_cast<uintptr_t>(h.obj) | reinterpret_cast<uintptr_t>(h.cls)) & 15u) return;
+        const cuuint32_t estr[3] = {1, 1, 1};
+        {
+            const cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)A, (cuuint64_t)p.B};
+            const cuuint64_t strides[2] = {(cuuint64_t)HW * 4, (cuuint64_t)(A * HW) * 4};
+            const cuuint32_t box[3] = {(cuuint32_t)WT_CELLS, 1, 1};
+            if (encode(&p.tma_obj[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(h.obj), dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return;
+        }
+        {
+            const cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)(A * C), (cuuint64_t)p.B};
+            const cuuint64_t strides[2] = {(cuuint64_t)HW * 4, (cuuint64_t)(A * C * HW) * 4};
+            const cuuint32_t box[3] = {(cuuint32_t)WT_CELLS, (cuuint32_t)nq, 1};
+            if (encode(&p.tma_cls[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(h.cls), dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return;
+        }
+    }
+    p.use_tma = 1;
+}
+
 extern "C" int64_t kodb_eval_workspace_bytes(int32_t batch, int64_t rows_per_image, int32_t num_classes) {
     // upper bound of chunks per image: tiles <= ceil(rows/256) + one ragged tile per (level, anchor) plane
     const int tiles = (int)((rows_per_image + kodb::WT_CELLS - 1) / kodb::WT_CELLS) + KODB_NUM_LEVELS * KODB_MAX_ANCHORS;
@@ -2064,6 +2142,7 @@ extern "C" int kodb_eval_tail(const kodb_head_level* heads_h, const kodb_level_c
     p.chunks_per_image = tiles * p.ngroups;
     p.trace = nullptr;
     p.floor_mode = vec == 4;
+    p.use_tma = 0;
     p.sample_stride = (tiles + CW_WARPS - 1) / CW_WARPS;  // at most one sample tile per warp of the sample CTA
     p.ns = (tiles + p.sample_stride - 1) / p.sample_stride;
     p.magic_b = magic_div((unsigned)batch, (uint64_t)tiles * batch + CW_WARPS);
@@ -2089,6 +2168,7 @@ extern "C" int kodb_eval_tail(const kodb_head_level* heads_h, const kodb_level_c
         if (vec == 4) {
             const dim3 grid((unsigned)(batch + ((int64_t)(tiles - p.ns) * batch + CW_WARPS - 1) / CW_WARPS));
             const int nq = p.C < CGROUP ? p.C : CGROUP;
+            setup_cand_tma(p, nq <= 4 ? 4 : nq <= 8 ? 8 : nq <= 10 ? 10 : nq <= 12 ? 12 : 16);
             rc = nq <= 4 ? launch_cand_warp<4>(p, grid, st) : nq <= 8 ? launch_cand_warp<8>(p, grid, st)
                  : nq <= 10 ? launch_cand_warp<10>(p, grid, st) : nq <= 12 ? launch_cand_warp<12>(p, grid, st)
                                                                             : launch_cand_warp<16>(p, grid, st);
@@ -2125,6 +2205,7 @@ extern "C" int kodb_nms(const float* detections, int32_t batch, int64_t rows, co
     p.chunks_per_image = p.tiles_per_image * p.ngroups;
     p.trace = nullptr;
     p.floor_mode = 0;
+    p.use_tma = 0;
     p.ns = 0;
     p.sample_stride = 1;
     p.magic_b = p.magic_s1 = 0u;
@@ -2168,3 +2249,4 @@ extern "C" int kodb_map_match(const float* dets, const int32_t* counts, int32_t 
     KODB_CHECK_LAUNCH();
     return KODB_OK;
 }
+static_assert(sizeof(kodb::EvalParams) <= 4000, "kernel parameter space");

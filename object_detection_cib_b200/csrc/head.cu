@@ -15,12 +15,12 @@
 //     epilogue (tcgen05.ld 32x32b: thread = cell, registers = channels; + bias; stores are 128-byte coalesced along the
 //     cells of ONE output plane, which is precisely the planar layout the detection tail wants).
 // HBM-bound by construction (AI ~ 17 flop/B at K=128, N=45): 4*K bytes in + 4*N bytes out per cell.
-#include <cuda.h>  // CUtensorMap + enums only; the encoder entry point is fetched at run time (no libcuda link dependency)
 #include <stdlib.h>
 
 #include <mutex>
 
 #include "kodb_common.cuh"
+#include "tma_common.cuh"
 
 namespace kodb {
 
@@ -62,50 +62,7 @@ struct HeadParams {
     int order[KODB_NUM_LEVELS];  // levels by descending K: the heavy tiles lead the static round-robin
 };
 
-// ---- PTX wrappers ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// bounded: a broken pipeline must not hang the GPU (a trap surfaces as a launch error on the host)
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
-        if (spins > (1u << 26)) __trap();
-    }
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
+// ---- PTX wrappers (mbarrier / TMA: tma_common.cuh) ---------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // D[tmem] (+)= A[smem desc] * B[smem desc], tf32 inputs, fp32 accumulate, issued by ONE thread for the CTA
@@ -178,7 +135,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_forward_kernel(const __gri
             mbar_init(tfull_bar + a, 1);
             mbar_init(tempty_bar + a, HD_EPI_WARPS);  // one arrival per epilogue warp
         }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
     }
     if (warp == 1) {  // TMEM: two accumulators of acc_cols columns; this warp owns allocation and release
         const uint32_t ncols = 2u * (uint32_t)p.acc_cols;
@@ -391,24 +348,6 @@ __global__ void __launch_bounds__(HG_THREADS) head_generic_kernel(const __grid_c
 }
 
 // ---- host -----------------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encoder() {
-    static EncodeTiledFn fn = nullptr;
-    static std::mutex mu;
-    std::lock_guard<std::mutex> lock(mu);
-    if (!fn) {
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(ptr);
-    }
-    return fn;
-}
-
 }  // namespace kodb
 
 extern "C" int kodb_head_forward(const kodb_head_conv_level* levels_h, int32_t num_levels, int32_t batch, int32_t num_anchors,
@@ -419,7 +358,7 @@ extern "C" int kodb_head_forward(const kodb_head_conv_level* levels_h, int32_t n
         return KODB_ERR_INVALID_ARGUMENT;
     const int n3 = num_anchors * (5 + num_classes);
     const int n_pad = (n3 + 15) / 16 * 16;
-    EncodeTiledFn encode = get_encoder();
+    EncodeTiledFn encode = tensormap_encoder();
     cudaStream_t st = (cudaStream_t)stream;
     HeadParams p;
     p.n_pad = n_pad;
