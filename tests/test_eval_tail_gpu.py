@@ -369,6 +369,30 @@ def test_matching_and_ap(B, S, C, dtype, oracle_lib):
     assert abs(got2["avg_mAP"] - want["avg_mAP"]) < 1e-4
 
 
+@pytest.mark.parametrize("B,S,C", [(3, 640, 10), (2, 320, 80)])
+def test_fused_eval_tail_strided_heads(B, S, C):
+    """Head tensors that are not flat planar arrays (every other image of a larger batch: batch stride 2x): the candidate
+    kernel's TMA tile loads do not apply and the per-lane cp.async path runs -- same keeps, rows and records, bit for bit,
+    as on a contiguous copy of the same images."""
+    heads2 = syn.make_head(2 * B, S, C, seed=31 + C)
+    targets = syn.make_targets(B, S, C, seed=8, n_min=1, n_max=9)
+    dev2 = _to_dev(heads2)
+    strided = [DetectionHeadResult(*[t[::2] for t in lv]) for lv in dev2]
+    packed = [DetectionHeadResult(*[t.permute(0, 1, 4, 2, 3).contiguous().permute(0, 1, 3, 4, 2) for t in lv]) for lv in strided]
+    assert not strided[0].cls.permute(0, 1, 4, 2, 3).is_contiguous() and packed[0].cls.permute(0, 1, 4, 2, 3).is_contiguous()
+    info = default_anchor_info()
+    out = []
+    for hv in (packed, strided):
+        ev = DeviceCocoMapEvaluator(C, device=DEV)
+        res, rec = N.eval_tail(FeatureShape(S, S), hv, info, 0.001, 0.6, targets=targets, gt_count=ev.gt_count)
+        out.append((res, rec))
+    (r0, m0), (r1, m1) = out
+    assert torch.equal(r0.counts, r1.counts) and int(r0.counts.min()) > 0
+    assert torch.equal(r0.keep_idx, r1.keep_idx)
+    assert torch.equal(r0.dets, r1.dets)
+    assert torch.equal(m0.tp, m1.tp) and torch.equal(m0.score, m1.score)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
 def test_matching_crowded_image(dtype, oracle_lib):
     """One image with more ground-truth boxes than the select kernel stages in shared memory (512): the matching runs
