@@ -85,6 +85,51 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def hbm_probe(dev, mb=96, nbuf=4, reps=20):
+    """Context for the roofline fractions, measured live with plain torch kernels on buffers of the step's size (rotating
+    over `nbuf` buffers > L2): a pure write stream (fill), a pure read stream (sum) and a copy, each alone, and the fill
+    and the read as two concurrent streams -- on this GPU a read stream and a write stream share the HBM and do not overlap
+    (tools/micro/rw_mix.cu), which is why the step's streaming kernels add up."""
+    import torch
+    n = mb * (1 << 20) // 4
+    bufs = [torch.empty(n, dtype=torch.float32, device=dev).normal_() for _ in range(nbuf)]
+    dst = [torch.empty(n, dtype=torch.float32, device=dev) for _ in range(nbuf)]
+    outs = torch.empty(nbuf, dtype=torch.float32, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fa, fb=None):
+        best = None
+        for _ in range(3):
+            torch.cuda.synchronize(dev)
+            cur = torch.cuda.current_stream(dev)
+            e0.record(cur)
+            s1.wait_stream(cur); s2.wait_stream(cur)
+            for i in range(reps):
+                with torch.cuda.stream(s1):
+                    fa(i % nbuf)
+                if fb is not None:
+                    with torch.cuda.stream(s2):
+                        fb(i % nbuf)
+            cur.wait_stream(s1); cur.wait_stream(s2)
+            e1.record(cur)
+            torch.cuda.synchronize(dev)
+            t = e0.elapsed_time(e1) / reps
+            best = t if best is None else min(best, t)
+        return best
+
+    fill = lambda i: dst[i].zero_()
+    read = lambda i: torch.sum(bufs[i], dim=0, out=outs[i])
+    copy = lambda i: dst[i].copy_(bufs[i])
+    b = mb * (1 << 20)
+    t_f, t_r, t_c, t_fr = timed(fill), timed(read), timed(copy), timed(fill, read)
+    gbs = lambda nbytes, ms: round(nbytes / (ms * 1e-3) / 1e9, 1)
+    return {"buffer_mb": mb, "fill_gbs": gbs(b, t_f), "read_gbs": gbs(b, t_r), "copy_gbs_read_plus_write": gbs(2 * b, t_c),
+            "fill_and_read_concurrent_gbs_total": gbs(2 * b, t_fr), "fill_us": round(t_f * 1e3, 2), "read_us": round(t_r * 1e3, 2),
+            "fill_and_read_concurrent_us": round(t_fr * 1e3, 2),
+            "note": "torch kernels (zero_, sum, copy_) on rotating buffers > L2; concurrent = two streams"}
+
+
 # ------------------------------------------------------------------------------------------------------
 # clocks sampling (nvidia-smi) during the loaded regions
 # ------------------------------------------------------------------------------------------------------
@@ -705,6 +750,11 @@ def run_ours(a):
             "map_report": {k: report[k] for k in ("avg_mAP", "mAP_50")}, "map_check": map_check,
             "extra_configs": extra,
         }
+        if world == 1 and not a.no_extra:
+            try:
+                line["roofline"]["hbm_probe"] = hbm_probe(dev)
+            except Exception as e:  # pragma: no cover
+                line["roofline"]["hbm_probe"] = {"error": str(e)[:200]}
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(a, a.cpu_sample)
         print(json.dumps(line), flush=True)
