@@ -29,6 +29,8 @@
 #include <stddef.h>
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "kodb_common.cuh"
 #include "tma_common.cuh"
 
@@ -379,6 +381,9 @@ __device__ __forceinline__ unsigned long long expand_nibbles(unsigned a16) {  //
 }
 
 constexpr int HOT_TARGET = 2048;
+
+// host-side caches (function attributes per device, tuning knobs) are shared by every host thread that calls into the library
+static std::mutex g_eval_host_mu;
 
 // smallest positive score of coarse bin d (d < HB - 1)
 __device__ __forceinline__ float coarse_lower_edge(int d) { return __uint_as_float(((0x3F800000u >> 18) - (uint32_t)d) << 18); }
@@ -792,6 +797,7 @@ template <int NQ>
 static int launch_cand_warp(const EvalParams& p, dim3 grid, cudaStream_t st) {
     const size_t smem = sizeof(CandWarpSmem<NQ>) * CW_WARPS + 128;  // (+ alignment of the stashes)
     static bool attr_set[64] = {false};
+    std::lock_guard<std::mutex> host_lock(g_eval_host_mu);
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
@@ -1898,6 +1904,7 @@ static int launch_match_crowded(const float* dets, const int32_t* counts, int ba
         return KODB_ERR_CAPACITY;
     }
     static bool attr_set[64] = {false};
+    std::lock_guard<std::mutex> host_lock(g_eval_host_mu);
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
@@ -2041,6 +2048,7 @@ static int launch_select(const EvalParams& p_in, cudaStream_t st) {
     p.trace = g_trace;
     const size_t smem = kNmsRegion + sizeof(GtSmem);
     static bool attr_set[64] = {false};
+    std::lock_guard<std::mutex> host_lock(g_eval_host_mu);
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
@@ -2077,6 +2085,7 @@ static void setup_cand_tma(kodb::EvalParams& p, int nq) {
     using namespace kodb;
     p.use_tma = 0;
     static int knob = -1;
+    std::lock_guard<std::mutex> host_lock(g_eval_host_mu);
     if (knob < 0) {
         const char* e = getenv("KODB_EVAL_TMA");
         knob = e ? (atoi(e) != 0) : 1;
@@ -2148,7 +2157,7 @@ extern "C" int kodb_eval_tail(const kodb_head_level* heads_h, const kodb_level_c
     p.magic_b = magic_div((unsigned)batch, (uint64_t)tiles * batch + CW_WARPS);
     p.magic_s1 = p.sample_stride > 1 ? magic_div((unsigned)(p.sample_stride - 1), (uint64_t)tiles) : 0u;
     static bool env_read = false;
-    if (!env_read) {  // tuning knob (like KODB_TRAIN_DENSE_PER_SM); the debug hook overrides it
+    if (std::lock_guard<std::mutex> host_lock(g_eval_host_mu); !env_read) {  // tuning knob (like KODB_TRAIN_DENSE_PER_SM); the debug hook overrides it
         env_read = true;
         const char* e = getenv("KODB_HOT_TARGET");
         if (e && atoi(e) > 0) g_hot_target = atoi(e);
@@ -2237,6 +2246,7 @@ extern "C" int kodb_map_match(const float* dets, const int32_t* counts, int32_t 
     if (gt_h->max_per_image > GT_CAP)
         return launch_match_crowded(dets, counts, batch, max_det, num_classes, gt_h, match_h, (cudaStream_t)stream);
     static bool attr_set[64] = {false};
+    std::lock_guard<std::mutex> host_lock(g_eval_host_mu);
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
