@@ -190,6 +190,16 @@ typedef struct kodb_head_conv_level {
 int kodb_head_forward(const kodb_head_conv_level* levels_h /* [num_levels], 1..3 */, int32_t num_levels, int32_t batch,
                       int32_t num_anchors, int32_t num_classes, void* stream);
 
+/* kodb_head_detections: the eval side of the same GEMM -- get_detections(Yolov5Head.forward(x)) (exp.py:70-102 on top of
+ * yolov5.py:170-178) in ONE launch: the epilogue decodes the accumulators (sigmoid / grid / anchor, layers.py:55-89) and
+ * writes the (B, AC, 5+C) detection rows (rows ll|ml|hl, r = (a*H+y)*W+x; columns x1,y1,x2,y2,sigmoid(obj),sigmoid(cls));
+ * the planar logits are never written (out_* of the levels are ignored).  level_cfg_h[l] gives stride / anchors / grid of
+ * levels_h[l].  Tensor-core path only: KODB_ERR_UNSUPPORTED for a level outside it (see kodb_head_forward; callers then
+ * run kodb_head_forward + kodb_decode). */
+int kodb_head_detections(const kodb_head_conv_level* levels_h /* [num_levels] */, const kodb_level_cfg* level_cfg_h,
+                         int32_t num_levels, int32_t batch, int32_t num_anchors, int32_t num_classes, float* detections,
+                         void* stream);
+
 /* kodb_sgd_step: one optimizer step of torch.optim.SGD(momentum, nesterov) over SmartOptimizer's parameter groups
  * (kod/nn/optim/smart.py:11-60) with the per-group lr / momentum of the warm-up updater
  * (kod/lightning/experiments/yv5_baseline/warmup.py:11-58).  params / grads / momentum are flat fp32 arenas holding

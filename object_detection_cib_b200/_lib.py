@@ -109,6 +109,8 @@ SIGNATURES = {
                                   C.POINTER(GradLevel), _P, _P, _P, C.c_int64, _P]),
     "kodb_iou_aligned": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_float, _P, _P, _P, _P, _P]),
     "kodb_head_forward": (C.c_int, [C.POINTER(HeadConvLevel), C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "kodb_head_detections": (C.c_int, [C.POINTER(HeadConvLevel), C.POINTER(LevelCfg), C.c_int32, C.c_int32, C.c_int32,
+                                       C.c_int32, _P, _P]),
     "kodb_sgd_step": (C.c_int, [_P, _P, _P, C.POINTER(C.c_int64), C.c_int32, _P, C.c_int32, C.c_int32, _P]),
     "kodb_decode": (C.c_int, [C.POINTER(HeadLevel), C.POINTER(LevelCfg), C.c_int32, C.c_int32, _P, _P]),
     "kodb_eval_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int64, C.c_int32]),

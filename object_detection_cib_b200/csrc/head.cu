@@ -49,6 +49,10 @@ struct HeadLevelParams {
     int n1, n2, n3;      // channel boundaries: box [0, n1), objectness [n1, n2), class [n2, n3)
     float* out[3];       // planar [B][channels][HW]
     const float* bias[3];
+    // decode epilogue (kodb_head_detections): geometry of the level in the (B, AC, 5+C) detection tensor
+    int row_base, W;
+    float stride;
+    float anchor_px[KODB_MAX_ANCHORS][2];
 };
 
 struct HeadParams {
@@ -60,6 +64,9 @@ struct HeadParams {
     int b_stage_bytes;   // n_pad * 128
     int total_units;
     int order[KODB_NUM_LEVELS];  // levels by descending K: the heavy tiles lead the static round-robin
+    // decode epilogue: instead of the planar logits the epilogue writes get_detections' rows (exp.py:70-102)
+    float* det;          // (B, rows_total, 5+C) or null
+    int rows_total, A, C;
 };
 
 // ---- PTX wrappers (mbarrier / TMA: tma_common.cuh) ---------------------------------------------------------------------
@@ -86,6 +93,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, leading / stride byte offsets in
@@ -106,6 +120,7 @@ __device__ __forceinline__ int unit_level(const HeadParams& p, int u) {
     return u >= p.lv[p.order[2]].unit_begin ? p.order[2] : (u >= p.lv[p.order[1]].unit_begin ? p.order[1] : p.order[0]);
 }
 
+template <bool DECODE>
 __global__ void __launch_bounds__(HD_THREADS, 1) head_forward_kernel(const __grid_constant__ HeadParams p) {
     extern __shared__ __align__(1024) uint8_t hd_smem_raw[];
     // 1024-byte alignment of every operand stage (128B swizzle atoms are 1 KB)
@@ -119,6 +134,8 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_forward_kernel(const __gri
     uint64_t* tempty_bar = bars + 2 * HD_STAGES + 2;  // [2]      epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * HD_STAGES + 4);
     HeadChannel* chan = reinterpret_cast<HeadChannel*>(bars + 2 * HD_STAGES + 6);  // [KODB_NUM_LEVELS][n_pad]
+    // decode epilogue: per epilogue warp a 32 rows x 16 columns staging tile (pitch 17: conflict-free both ways)
+    float* det_stage = reinterpret_cast<float*>(chan + KODB_NUM_LEVELS * p.n_pad);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -151,7 +168,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_forward_kernel(const __gri
             const int ti = n < L.n1 ? 0 : (n < L.n2 ? 1 : 2);
             const int nb = ti == 0 ? 0 : (ti == 1 ? L.n1 : L.n2);
             const int ch = ti == 0 ? L.n1 : (ti == 1 ? L.n2 - L.n1 : L.n3 - L.n2);
-            c.base = L.out[ti] + (size_t)(n - nb) * L.HW;
+            c.base = L.out[ti] ? L.out[ti] + (size_t)(n - nb) * L.HW : nullptr;
             c.img_stride = (uint32_t)(ch * L.HW);
             c.bias = __ldg(L.bias[ti] + (n - nb));
         }
@@ -247,6 +264,69 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_forward_kernel(const __gri
                 mbar_wait(tfull_bar + acc, acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * p.acc_cols);
+                if constexpr (DECODE) {
+                    // ---- decode epilogue: rows of get_detections (x1, y1, x2, y2, sigmoid(obj), sigmoid(cls...)) ----
+                    // anchors alternate between the two warps of a lane quadrant; a row's 5+C columns go out in chunks of
+                    // 16 through the warp's staging tile, so that global stores are 64-byte runs of consecutive rows
+                    const int A = p.A, C = p.C, cols = 5 + C;
+                    float* st = det_stage + (warp - 2) * (32 * 17);
+                    const int gy = cell / L.W, gx = cell - gy * L.W;
+                    const int nrow = min(32, L.HW - (c0 + 32 * q));  // live rows of this warp (<= 0: none)
+                    for (int a = half; a < A; a += 2) {
+                        const int cls0 = 5 * A + a * C;  // first class column of the anchor in the accumulator
+                        float* dst = p.det + ((size_t)b * p.rows_total + L.row_base + (size_t)a * L.HW + c0 + 32 * q) * cols;
+                        for (int j0 = 0; j0 < cols; j0 += 16) {
+                            const int nc = min(16, cols - j0);
+                            float val[16];
+                            const int col = j0 == 0 ? cls0 : cls0 + j0 - 5;  // first class column of this chunk
+                            const int ncls = j0 == 0 ? nc - 5 : nc;
+                            uint32_t v[16];
+                            if (col + 16 <= p.acc_cols) {
+                                tmem_ld16(taddr + col, v);
+                            } else {  // the 16-column read would leave the accumulator: column by column
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) {
+                                    v[i] = 0u;
+                                    if (i < ncls) tmem_ld1(taddr + col + i, v[i]);
+                                }
+                            }
+                            if (j0 == 0) {
+                                uint32_t vb[4], vo;
+                                tmem_ld4(taddr + 4 * a, vb);
+                                tmem_ld1(taddr + 4 * A + a, vo);
+                                tmem_ld_wait();
+                                const float4 bx = decode_box(__uint_as_float(vb[0]) + tab[4 * a].bias, __uint_as_float(vb[1]) + tab[4 * a + 1].bias,
+                                                             __uint_as_float(vb[2]) + tab[4 * a + 2].bias, __uint_as_float(vb[3]) + tab[4 * a + 3].bias,
+                                                             (float)gx, (float)gy, L.stride, L.anchor_px[a][0], L.anchor_px[a][1]);
+                                val[0] = bx.x; val[1] = bx.y; val[2] = bx.z; val[3] = bx.w;
+                                val[4] = sigmoid_eval(__uint_as_float(vo) + tab[4 * A + a].bias);
+#pragma unroll
+                                for (int i = 0; i < 11; ++i)
+                                    val[5 + i] = i < ncls ? sigmoid_eval(__uint_as_float(v[i]) + tab[min(col + i, n3 - 1)].bias) : 0.0f;
+                            } else {
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int i = 0; i < 16; ++i)
+                                    val[i] = i < ncls ? sigmoid_eval(__uint_as_float(v[i]) + tab[min(col + i, n3 - 1)].bias) : 0.0f;
+                            }
+                            __syncwarp();  // the previous chunk's readers of the staging tile are done
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (i < nc) st[lane * 17 + i] = val[i];
+                            __syncwarp();
+                            for (int i = lane; i < nrow * nc; i += 32) {
+                                const int rr = i / nc, cc = i - rr * nc;
+                                dst[(size_t)rr * cols + j0 + cc] = st[rr * 17 + cc];
+                            }
+                        }
+                    }
+                    // every tcgen05.ld of this warp has completed (wait::ld above): hand the accumulator back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar + acc);
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                    continue;
+                }
                 int n0 = 16 * half;
                 if (n0 >= n3) {  // nothing to read for this warp: hand the accumulator back at once
                     tc_fence_before();
@@ -350,8 +430,10 @@ __global__ void __launch_bounds__(HG_THREADS) head_generic_kernel(const __grid_c
 // ---- host -----------------------------------------------------------------------------------------------------------
 }  // namespace kodb
 
-extern "C" int kodb_head_forward(const kodb_head_conv_level* levels_h, int32_t num_levels, int32_t batch, int32_t num_anchors,
-                                 int32_t num_classes, void* stream) {
+// det == nullptr: planar logits (Yolov5Head.forward); det != nullptr: decoded detections (get_detections of those logits),
+// level_cfg_h gives each level's stride / anchors / grid
+static int head_launch(const kodb_head_conv_level* levels_h, int32_t num_levels, int32_t batch, int32_t num_anchors,
+                       int32_t num_classes, const kodb_level_cfg* level_cfg_h, float* det, void* stream) {
     using namespace kodb;
     if (!levels_h || num_levels < 1 || num_levels > KODB_NUM_LEVELS || batch < 1 || num_anchors < 1 || num_anchors > KODB_MAX_ANCHORS || num_classes < 1 ||
         num_classes > KODB_MAX_CLASSES)
@@ -367,17 +449,18 @@ extern "C" int kodb_head_forward(const kodb_head_conv_level* levels_h, int32_t n
     p.b_stage_bytes = n_pad * 128;
     // A operand (MN-major tf32): the only legal shared-memory layout is the 128-byte swizzle with a 32-byte atom
     // (cutlass sm100_common.inl:92; UMMA layout type SWIZZLE_128B_BASE32B)
-    int tiles = 0, n_tc = 0;
+    int tiles = 0, n_tc = 0, det_rows = 0;
     for (int li = 0; li < num_levels; ++li) {
         const kodb_head_conv_level& h = levels_h[li];
-        if (!h.x || !h.weight || !h.out_box || !h.out_obj || !h.out_cls || !h.bias_box || !h.bias_obj || !h.bias_cls ||
-            h.in_channels < 1 || h.H < 1 || h.W < 1)
+        if (!h.x || !h.weight || !h.bias_box || !h.bias_obj || !h.bias_cls || h.in_channels < 1 || h.H < 1 || h.W < 1)
             return KODB_ERR_INVALID_ARGUMENT;
+        if (!det && (!h.out_box || !h.out_obj || !h.out_cls)) return KODB_ERR_INVALID_ARGUMENT;
         const int HW = h.H * h.W;
         // the tensor-core path needs: 32-channel k-blocks, 16-byte global strides for the TMA (H*W % 4), 16-byte aligned
         // bases, one UMMA tile in N (A*(5+C) <= 256: three anchors up to 80 classes)
         const bool tc = encode && n_pad <= 256 && h.in_channels % HD_KB == 0 && HW % 4 == 0 &&
                         !((reinterpret_cast<uintptr_t>(h.x) | reinterpret_cast<uintptr_t>(h.weight)) & 15u);
+        if (!tc && det) return KODB_ERR_UNSUPPORTED;  // the decode epilogue exists on the tensor-core path only
         if (!tc) {  // small / odd level: the SIMT kernel
             HeadGenericParams g;
             g.x = h.x;
@@ -406,8 +489,18 @@ extern "C" int kodb_head_forward(const kodb_head_conv_level* levels_h, int32_t n
         L.n1 = num_anchors * 4;
         L.n2 = L.n1 + num_anchors;
         L.n3 = n3;
-        L.out[0] = h.out_box; L.out[1] = h.out_obj; L.out[2] = h.out_cls;
+        L.out[0] = det ? nullptr : h.out_box; L.out[1] = det ? nullptr : h.out_obj; L.out[2] = det ? nullptr : h.out_cls;
         L.bias[0] = h.bias_box; L.bias[1] = h.bias_obj; L.bias[2] = h.bias_cls;
+        L.row_base = det_rows;
+        L.W = h.W;
+        L.stride = 0.f;
+        if (det) {
+            const kodb_level_cfg& c = level_cfg_h[li];
+            if (c.H != h.H || c.W != h.W || c.num_anchors != num_anchors) return KODB_ERR_INVALID_ARGUMENT;
+            L.stride = (float)c.stride;
+            for (int a = 0; a < num_anchors; ++a) { L.anchor_px[a][0] = c.anchor_px[a][0]; L.anchor_px[a][1] = c.anchor_px[a][1]; }
+            det_rows += num_anchors * HW;
+        }
         {   // feature map (B, K, H, W) as (cell, channel, image)
             const cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)h.in_channels, (cuuint64_t)batch};
             const cuuint64_t strides[2] = {(cuuint64_t)HW * 4, (cuuint64_t)HW * 4 * h.in_channels};
@@ -447,8 +540,12 @@ extern "C" int kodb_head_forward(const kodb_head_conv_level* levels_h, int32_t n
         if (L.tiles > 0) units += (L.tiles + L.per_unit - 1) / L.per_unit;
     }
     p.total_units = units;
+    p.det = det;
+    p.rows_total = det_rows;
+    p.A = num_anchors;
+    p.C = num_classes;
     const size_t smem = 1024 + (size_t)HD_STAGES * (HD_A_STAGE_BYTES + p.b_stage_bytes) + 256 +
-                        (size_t)KODB_NUM_LEVELS * n_pad * sizeof(HeadChannel);
+                        (size_t)KODB_NUM_LEVELS * n_pad * sizeof(HeadChannel) + (det ? (size_t)HD_EPI_WARPS * 32 * 17 * sizeof(float) : 0);
     static std::mutex mu;
     static size_t smem_set[64] = {0};
     static int sms[64] = {0};
@@ -458,7 +555,8 @@ extern "C" int kodb_head_forward(const kodb_head_conv_level* levels_h, int32_t n
     {
         std::lock_guard<std::mutex> lock(mu);
         if (smem_set[dev] < smem) {
-            if (cudaFuncSetAttribute(head_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            if (cudaFuncSetAttribute(head_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+                cudaFuncSetAttribute(head_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
                 return KODB_ERR_LAUNCH;
             smem_set[dev] = smem;
         }
@@ -469,10 +567,22 @@ extern "C" int kodb_head_forward(const kodb_head_conv_level* levels_h, int32_t n
         }
     }
     // persistent: as many CTAs as fit (shared memory: two per SM with the small class head, one with 80 classes)
-    const int per_sm = smem <= 110 * 1024 ? 2 : 1;
+    const int per_sm = smem <= 112 * 1024 ? 2 : 1;
     int grid = sms[dev] * per_sm;
     if (grid > units) grid = units;
-    head_forward_kernel<<<grid, HD_THREADS, smem, st>>>(p);
+    if (det) head_forward_kernel<true><<<grid, HD_THREADS, smem, st>>>(p);
+    else head_forward_kernel<false><<<grid, HD_THREADS, smem, st>>>(p);
     KODB_CHECK_LAUNCH();
     return KODB_OK;
+}
+
+extern "C" int kodb_head_forward(const kodb_head_conv_level* levels_h, int32_t num_levels, int32_t batch, int32_t num_anchors,
+                                 int32_t num_classes, void* stream) {
+    return head_launch(levels_h, num_levels, batch, num_anchors, num_classes, nullptr, nullptr, stream);
+}
+
+extern "C" int kodb_head_detections(const kodb_head_conv_level* levels_h, const kodb_level_cfg* level_cfg_h, int32_t num_levels,
+                                    int32_t batch, int32_t num_anchors, int32_t num_classes, float* detections, void* stream) {
+    if (!level_cfg_h || !detections) return KODB_ERR_INVALID_ARGUMENT;
+    return head_launch(levels_h, num_levels, batch, num_anchors, num_classes, level_cfg_h, detections, stream);
 }

@@ -7,6 +7,9 @@ once and writes the three planar `[B][A*P][H][W]` tensors the detection tail con
   same bias initialisation (yolov5.py:62-75, :111-123), same output `DetectionHeadResult(box, obj, cls)` of
   `(B, A, H, W, P)` views.
 * `fused_heads_forward(heads, xs)` – all (up to three) levels in ONE launch.
+* `fused_heads_detections(heads, xs, image_feature_shape, anchor_info)` – the eval side: `get_detections` (exp.py:70-102) of
+  those head outputs in the SAME launch – the GEMM's epilogue decodes the accumulators (sigmoid / grid / anchor) and writes
+  the `(B, AC, 5+C)` rows; the planar logits are never written.  No gradient (inference / validation).
 * Backward: dX / dW / db with library GEMMs (cuBLAS through torch) – the gradients of the planar tensors come straight
   from the train tail, already in the layout the GEMMs want.
 Precision: fp32 in, tf32 multiply, fp32 accumulate, i.e. what torch's default convolution policy
@@ -121,6 +124,56 @@ def fused_heads_forward(heads: Sequence["Yolov5Head"], xs: Sequence[torch.Tensor
         res.append(DetectionHeadResult(*[t.view(t.shape[0], A, t.shape[1] // A, t.shape[2], t.shape[3]).permute(0, 1, 3, 4, 2)
                                          for t in planes]))
     return res
+
+
+def _level_args(heads, xs):
+    """ctypes level array + the tensors that must stay alive during the launch."""
+    n_lv = len(heads)
+    arr = (L.HeadConvLevel * n_lv)()
+    keep = []
+    for l, (h, x) in enumerate(zip(heads, xs)):
+        H.require_cuda(x, "feature map")
+        if x.dtype != torch.float32:
+            raise TypeError("the head runs in float32 (tf32 tensor cores), like the reference")
+        x = x.detach().contiguous()
+        K = x.shape[1]
+        ws = [m.conv.weight.detach().reshape(m.conv.weight.shape[0], K) for m in (h.box_head, h.obj_head, h.cls_head)]
+        n = [w.shape[0] for w in ws]
+        base = ws[0].data_ptr()
+        if (all(w.is_contiguous() for w in ws) and ws[1].data_ptr() == base + n[0] * K * 4
+                and ws[2].data_ptr() == base + (n[0] + n[1]) * K * 4 and base % 16 == 0):
+            w_all = ws[0]
+        else:
+            w_all = torch.cat(ws, 0)
+        a = arr[l]
+        a.x, a.weight = x.data_ptr(), w_all.data_ptr()
+        a.bias_box, a.bias_obj, a.bias_cls = (m.conv.bias.data_ptr() for m in (h.box_head, h.obj_head, h.cls_head))
+        a.in_channels, a.H, a.W = K, x.shape[2], x.shape[3]
+        keep += [x, w_all]
+    return arr, keep
+
+
+def fused_heads_detections(heads: Sequence["Yolov5Head"], xs: Sequence[torch.Tensor], image_feature_shape, anchor_info) -> torch.Tensor:
+    """`get_detections(image_feature_shape, [head(x) for head, x in zip(heads, xs)])` (exp.py:70-102) in ONE launch: the
+    `(B, AC, 5+C)` detections straight from the feature maps.  Levels outside the tensor-core path (see the module
+    docstring) take two launches instead: planar logits, then the decode kernel."""
+    from . import nms as N
+    A, C = heads[0].num_anchors, heads[0].num_classes
+    levels = H.level_cfgs(anchor_info, image_feature_shape.width, image_feature_shape.height)
+    B, dev = xs[0].shape[0], xs[0].device
+    tc = all(x.shape[1] % 32 == 0 and (x.shape[2] * x.shape[3]) % 4 == 0 for x in xs) and A * (5 + C) <= 256
+    if not tc or len(heads) != L.NUM_LEVELS:
+        with torch.no_grad():
+            return N.get_detections(image_feature_shape, fused_heads_forward(heads, xs), anchor_info)
+    for lv, x in zip(levels, xs):
+        if (lv.H, lv.W) != (x.shape[2], x.shape[3]) or lv.num_anchors != A:
+            raise ValueError("feature maps do not match image_feature_shape // stride (layers.py:24-27)")
+    arr, keep = _level_args(heads, xs)
+    rows = sum(A * x.shape[2] * x.shape[3] for x in xs)
+    out = torch.empty((B, rows, 5 + C), dtype=torch.float32, device=dev)
+    L.check(L.lib().kodb_head_detections(arr, levels, len(heads), B, A, C, out.data_ptr(), H.stream_ptr(dev)),
+            "kodb_head_detections")
+    return out
 
 
 class Yolov5Head(nn.Module):

@@ -539,10 +539,36 @@ def head_cases():
     save("head_convs", **out)
 
 
+def head_detect_cases():
+    """Features -> reference Yolov5Head x3 -> reference get_detections (exp.py:70-102): the fused eval epilogue's target."""
+    from kod.nn.heads.yolov5 import Yolov5Head
+    B, C, A, S = 2, 10, 3, 128
+    g = torch.Generator().manual_seed(191)
+    out = {"meta": np.array([B, C, A, S], np.int64)}
+    chans = (64, 128, 256)
+    res = []
+    for l, (K, stride) in enumerate(zip(chans, syn.STRIDES)):
+        torch.manual_seed(192 + l)
+        head = Yolov5Head(in_channels=K, num_anchors_per_cell=A, num_classes=C, stride=stride)
+        x = torch.randn(B, K, S // stride, S // stride, generator=g)
+        with torch.no_grad():
+            r = head(x)
+        res.append(r)
+        out[f"l{l}/x"] = x.numpy()
+        for name, p in head.state_dict().items():
+            out[f"l{l}/param/{name}"] = p.numpy()
+    with torch.no_grad():
+        det = _Exp().get_detections(FeatureShape(width=S, height=S),
+                                    Yolov5NetworkResult(*[DetectionHeadResult(*[t.clone() for t in r]) for r in res]))
+    out["detections"] = det.numpy()
+    save("head_detect", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     if len(sys.argv) > 1 and sys.argv[1] == "head":
         head_cases()
+        head_detect_cases()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "augment":
         augment_cases()
@@ -565,3 +591,4 @@ if __name__ == "__main__":
     sgd_cases()
     augment_cases()
     head_cases()
+    head_detect_cases()

@@ -11,7 +11,7 @@ import torch
 import torch.nn.functional as F
 
 import _golden as G
-from object_detection_cib_b200.heads import Yolov5Head, fused_heads_forward
+from object_detection_cib_b200.heads import Yolov5Head, fused_heads_detections, fused_heads_forward
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -96,6 +96,44 @@ def test_head_odd_shapes_simt_kernel(K, Hh, Ww, C):
         torch.backends.cudnn.allow_tf32 = old
     sum(t.sum() for t in r).backward()
     assert x.grad is not None and torch.isfinite(x.grad).all()
+
+
+def test_head_detections_golden():
+    """Features -> detections in one launch (decode epilogue of the head GEMM) against the real reference's
+    Yolov5Head x3 + get_detections (fp32 CPU).  tf32 logits (|err| ~ 2e-3) go through sigmoid / (2 sigma)^2 * anchor:
+    probabilities to 1e-3, box corners to 5e-3 relative + 0.1 px."""
+    from object_detection_cib_b200.types import FeatureShape, default_anchor_info
+    g = G.load("head_detect")
+    B, C, A, S = (int(v) for v in g["meta"])
+    heads, xs = [], []
+    for l, stride in enumerate((8, 16, 32)):
+        x = torch.from_numpy(g[f"l{l}/x"]).to(DEV)
+        h = Yolov5Head(x.shape[1], A, C, stride).to(DEV)
+        h.load_state_dict({k[len(f"l{l}/param/"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith(f"l{l}/param/")})
+        heads.append(h)
+        xs.append(x)
+    det = fused_heads_detections(heads, xs, FeatureShape(S, S), default_anchor_info()).cpu().numpy()
+    want = g["detections"]
+    assert det.shape == want.shape
+    np.testing.assert_allclose(det[..., :4], want[..., :4], rtol=5e-3, atol=0.1)
+    np.testing.assert_allclose(det[..., 4:], want[..., 4:], rtol=0, atol=1e-3)
+
+
+@pytest.mark.parametrize("B,S,C", [(4, 640, 10), (2, 320, 80), (3, 416, 10)])
+def test_head_detections_equal_forward_then_decode(B, S, C):
+    """The decode epilogue and the two-launch path (planar logits, then kodb_decode) read the same accumulators and run the
+    same decode arithmetic: identical detections, bit for bit (416: a 13x13 level -> the wrapper takes the two-launch path)."""
+    from object_detection_cib_b200 import nms as N
+    from object_detection_cib_b200.types import FeatureShape, default_anchor_info
+    torch.manual_seed(S + C)
+    heads = [Yolov5Head(K, 3, C, s).to(DEV) for K, s in ((128, 8), (256, 16), (512, 32))]
+    xs = [torch.randn(B, K, S // s, S // s, device=DEV) for K, s in ((128, 8), (256, 16), (512, 32))]
+    info, shape = default_anchor_info(), FeatureShape(S, S)
+    det = fused_heads_detections(heads, xs, shape, info)
+    with torch.no_grad():
+        want = N.get_detections(shape, fused_heads_forward(heads, xs), info)
+    assert det.shape == want.shape == (B, sum(3 * (S // s) ** 2 for s in (8, 16, 32)), 5 + C)
+    assert torch.equal(det, want)
 
 
 def test_head_feeds_the_detection_tail():

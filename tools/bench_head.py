@@ -7,7 +7,9 @@ import torch
 import torch.nn.functional as F
 
 sys.path.insert(0, ".")
-from object_detection_cib_b200.heads import Yolov5Head, fused_heads_forward
+from object_detection_cib_b200 import nms as N
+from object_detection_cib_b200.heads import Yolov5Head, fused_heads_detections, fused_heads_forward
+from object_detection_cib_b200.types import FeatureShape, default_anchor_info
 
 B, S, C = (int(v) for v in sys.argv[1:4]) if len(sys.argv) > 3 else (64, 640, 10)
 dev = torch.device("cuda:0")
@@ -55,9 +57,15 @@ with torch.no_grad():
     got = fused_heads_forward(heads, xsets[0])
     want = ref(xsets[0])
     err = max(float((g.permute(0, 1, 4, 2, 3).reshape(w.shape) - w).abs().max()) for gl, wl in zip(got, want) for g, w in zip(gl, wl))
+with torch.no_grad():
+    info, shape = default_anchor_info(), FeatureShape(S, S)
+    t_det = timed(lambda xs: fused_heads_detections(heads, xs, shape, info))
+    t_two = timed(lambda xs: N.get_detections(shape, fused_heads_forward(heads, xs), info))
 n45 = 3 * (5 + C)
 bytes_in = sum(4 * B * K * (S // s) ** 2 for K, s in cfg)
 bytes_out = sum(4 * B * n45 * (S // s) ** 2 for K, s in cfg)
 print(f"head B={B} S={S} C={C}: fused {t_ours:.1f} us ({(bytes_in + bytes_out) / t_ours / 1e3:.0f} GB/s of {(bytes_in + bytes_out) / 1e6:.0f} MB, "
       f"frac of 6551 = {(bytes_in + bytes_out) / t_ours / 1e3 / 6551:.3f}); 3 cuDNN convs/level: tf32 {t_ref_tf32:.1f} us, fp32 {t_ref_fp32:.1f} us; "
       f"speed-up {t_ref_tf32 / t_ours:.2f}x / {t_ref_fp32 / t_ours:.2f}x; max |err| vs fp32 {err:.2e}")
+print(f"  features -> detections (decode epilogue): {t_det:.1f} us ({(bytes_in + bytes_out) / t_det / 1e3:.0f} GB/s, frac {(bytes_in + bytes_out) / t_det / 1e3 / 6551:.3f}); "
+      f"planar head + decode kernel: {t_two:.1f} us")
