@@ -770,7 +770,9 @@ def measure_head(B, S, Cn, peak, n=20, nsets=3):
     import torch
     import torch.nn.functional as F
 
-    from object_detection_cib_b200.heads import Yolov5Head, fused_heads_forward
+    from object_detection_cib_b200 import nms as N
+    from object_detection_cib_b200.heads import Yolov5Head, fused_heads_detections, fused_heads_forward
+    from object_detection_cib_b200.types import FeatureShape, default_anchor_info
 
     dev = torch.device("cuda", torch.cuda.current_device())
     cfg = ((128, 8), (256, 16), (512, 32))
@@ -808,6 +810,9 @@ def measure_head(B, S, Cn, peak, n=20, nsets=3):
             t_tf32 = timed(ref)
             torch.backends.cudnn.allow_tf32 = False
             t_fp32 = timed(ref)
+            info, shape = default_anchor_info(), FeatureShape(S, S)
+            t_det = timed(lambda xs: fused_heads_detections(heads, xs, shape, info))
+            t_two = timed(lambda xs: N.get_detections(shape, fused_heads_forward(heads, xs), info))
             got, want = fused_heads_forward(heads, xsets[0]), ref(xsets[0])
             err = max(float((g.permute(0, 1, 4, 2, 3).reshape(w.shape) - w).abs().max()) for gl, wl in zip(got, want) for g, w in zip(gl, wl))
     finally:
@@ -824,6 +829,12 @@ def measure_head(B, S, Cn, peak, n=20, nsets=3):
             "cudnn_tf32_ms_per_call": t_tf32, "cudnn_fp32_ms_per_call": t_fp32, "cudnn_launches_per_call": 9,
             "speedup_vs_cudnn_tf32": t_tf32 / t_ours, "speedup_vs_cudnn_fp32": t_fp32 / t_ours,
             "max_abs_err_vs_fp32_conv": err,
+            "eval_side": {"what": "features -> get_detections' (B, AC, 5+C) rows in ONE launch (kodb_head_detections: the same GEMM "
+                                  "with the decode epilogue; the planar logits are never written)",
+                          "ms_per_call": t_det, "achieved_gbs": (b_in + b_out) / (t_det * 1e-3) / 1e9,
+                          "frac": (b_in + b_out) / (t_det * 1e-3) / 1e9 / peak,
+                          "planar_head_then_decode_kernel_ms_per_call": t_two, "speedup_vs_two_launches": t_two / t_det,
+                          "speedup_vs_cudnn_tf32_convs_alone": t_tf32 / t_det},
             "roofline": {"bound": "hbm", "kernel": "head_forward_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "algorithmic_bytes_per_launch": b_in + b_out,
                          "note": "4*K bytes in + 4*3*(5+C) bytes out per cell; ~17 flop/B at K=128: HBM-bound, the tensor "

@@ -100,6 +100,19 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
 __device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& v) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
 }
+// Decode epilogue arithmetic: the logits come out of a tf32 GEMM (|error| ~ 2e-3), so the eval tail's bit-exact sigmoid
+// (libm expf + IEEE division, ~28 instructions) would buy nothing here; ex2.approx + rcp.approx (~1e-6 relative) keeps the
+// epilogue off the critical path.  Same expression tree as decode_box (kodb_common.cuh) otherwise.
+__device__ __forceinline__ float sigmoid_epi(float x) { return rcp_approx(1.0f + ex2_approx(-1.44269502162933349609375f * x)); }
+__device__ __forceinline__ float4 decode_box_epi(float p0, float p1, float p2, float p3, float gx, float gy, float stride,
+                                                 float aw_px, float ah_px) {
+    const float cx = ((sigmoid_epi(p0) * 2.0f + gx) - 0.5f) * stride;
+    const float cy = ((sigmoid_epi(p1) * 2.0f + gy) - 0.5f) * stride;
+    const float sw = sigmoid_epi(p2) * 2.0f, sh = sigmoid_epi(p3) * 2.0f;
+    const float w = (sw * sw) * aw_px, h = (sh * sh) * ah_px;
+    const float hw = 0.5f * w, hh = 0.5f * h;
+    return make_float4(cx - hw, cy - hh, cx + hw, cy + hh);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, leading / stride byte offsets in
@@ -121,7 +134,7 @@ __device__ __forceinline__ int unit_level(const HeadParams& p, int u) {
 }
 
 template <bool DECODE>
-__global__ void __launch_bounds__(HD_THREADS, 1) head_forward_kernel(const __grid_constant__ HeadParams p) {
+__global__ void __launch_bounds__(HD_THREADS, 2) head_forward_kernel(const __grid_constant__ HeadParams p) {
     extern __shared__ __align__(1024) uint8_t hd_smem_raw[];
     // 1024-byte alignment of every operand stage (128B swizzle atoms are 1 KB)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(hd_smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -295,19 +308,19 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_forward_kernel(const __gri
                                 tmem_ld4(taddr + 4 * a, vb);
                                 tmem_ld1(taddr + 4 * A + a, vo);
                                 tmem_ld_wait();
-                                const float4 bx = decode_box(__uint_as_float(vb[0]) + tab[4 * a].bias, __uint_as_float(vb[1]) + tab[4 * a + 1].bias,
+                                const float4 bx = decode_box_epi(__uint_as_float(vb[0]) + tab[4 * a].bias, __uint_as_float(vb[1]) + tab[4 * a + 1].bias,
                                                              __uint_as_float(vb[2]) + tab[4 * a + 2].bias, __uint_as_float(vb[3]) + tab[4 * a + 3].bias,
                                                              (float)gx, (float)gy, L.stride, L.anchor_px[a][0], L.anchor_px[a][1]);
                                 val[0] = bx.x; val[1] = bx.y; val[2] = bx.z; val[3] = bx.w;
-                                val[4] = sigmoid_eval(__uint_as_float(vo) + tab[4 * A + a].bias);
+                                val[4] = sigmoid_epi(__uint_as_float(vo) + tab[4 * A + a].bias);
 #pragma unroll
                                 for (int i = 0; i < 11; ++i)
-                                    val[5 + i] = i < ncls ? sigmoid_eval(__uint_as_float(v[i]) + tab[min(col + i, n3 - 1)].bias) : 0.0f;
+                                    val[5 + i] = i < ncls ? sigmoid_epi(__uint_as_float(v[i]) + tab[min(col + i, n3 - 1)].bias) : 0.0f;
                             } else {
                                 tmem_ld_wait();
 #pragma unroll
                                 for (int i = 0; i < 16; ++i)
-                                    val[i] = i < ncls ? sigmoid_eval(__uint_as_float(v[i]) + tab[min(col + i, n3 - 1)].bias) : 0.0f;
+                                    val[i] = i < ncls ? sigmoid_epi(__uint_as_float(v[i]) + tab[min(col + i, n3 - 1)].bias) : 0.0f;
                             }
                             __syncwarp();  // the previous chunk's readers of the staging tile are done
 #pragma unroll

@@ -120,9 +120,10 @@ def test_head_detections_golden():
 
 
 @pytest.mark.parametrize("B,S,C", [(4, 640, 10), (2, 320, 80), (3, 416, 10)])
-def test_head_detections_equal_forward_then_decode(B, S, C):
-    """The decode epilogue and the two-launch path (planar logits, then kodb_decode) read the same accumulators and run the
-    same decode arithmetic: identical detections, bit for bit (416: a 13x13 level -> the wrapper takes the two-launch path)."""
+def test_head_detections_vs_forward_then_decode(B, S, C):
+    """The decode epilogue and the two-launch path (planar logits, then kodb_decode) read the same accumulators; the epilogue
+    uses the approximate sigmoid (the logits are tf32 anyway), kodb_decode the exact one: probabilities agree to 1e-6
+    relative, box corners to 1e-3 px (416: a 13x13 level -> the wrapper takes the two-launch path itself: identical)."""
     from object_detection_cib_b200 import nms as N
     from object_detection_cib_b200.types import FeatureShape, default_anchor_info
     torch.manual_seed(S + C)
@@ -133,7 +134,11 @@ def test_head_detections_equal_forward_then_decode(B, S, C):
     with torch.no_grad():
         want = N.get_detections(shape, fused_heads_forward(heads, xs), info)
     assert det.shape == want.shape == (B, sum(3 * (S // s) ** 2 for s in (8, 16, 32)), 5 + C)
-    assert torch.equal(det, want)
+    if S == 416:
+        assert torch.equal(det, want)
+    else:
+        np.testing.assert_allclose(det[..., 4:].cpu().numpy(), want[..., 4:].cpu().numpy(), rtol=3e-6, atol=1e-9)
+        np.testing.assert_allclose(det[..., :4].cpu().numpy(), want[..., :4].cpu().numpy(), rtol=1e-5, atol=1e-3)
 
 
 def test_head_feeds_the_detection_tail():
