@@ -327,14 +327,18 @@ __global__ void __launch_bounds__(HD_THREADS, 2) head_forward_kernel(const __gri
                                 val[i] = i < ncls ? sigmoid_epi(__uint_as_float(v[i]) + tab[min(col + i, n3 - 1)].bias) : 0.0f;
                         }
                         __syncwarp();  // the previous chunk's readers of the staging tile are done
+                        // a row that fits one chunk (5 + C <= 16): staged at pitch = row length, so the warp's 32 rows are one
+                        // contiguous run in shared AND global memory -- a flat, fully coalesced copy without index arithmetic
+                        const bool whole = nc == cols;
+                        const int pitch = whole ? cols : 17;
 #pragma unroll
                         for (int i = 0; i < 16; ++i)
-                            if (i < nc) st[lane * 17 + i] = val[i];
+                            if (i < nc) st[lane * pitch + i] = val[i];
                         __syncwarp();
-                        if (nc == 16) {
+                        if (whole) {
+                            for (int i = lane; i < nrow * cols; i += 32) dst[i] = st[i];
+                        } else if (nc == 16) {
                             for (int i = lane; i < nrow * 16; i += 32) dst[(size_t)(i >> 4) * cols + j0 + (i & 15)] = st[(i >> 4) * 17 + (i & 15)];
-                        } else if (nc == 8) {
-                            for (int i = lane; i < nrow * 8; i += 32) dst[(size_t)(i >> 3) * cols + j0 + (i & 7)] = st[(i >> 3) * 17 + (i & 7)];
                         } else {
                             for (int i = lane; i < nrow * nc; i += 32) {
                                 const int rr = i / nc, cc = i - rr * nc;
