@@ -50,9 +50,13 @@ __global__ void __launch_bounds__(DEC_TILE) decode_kernel(const __grid_constant_
     __syncthreads();
     const int64_t row0 = (int64_t)p.row_base[L] + (int64_t)a * HW + c0;
     float* dst = p.out + ((int64_t)b * p.row_base[KODB_NUM_LEVELS] + row0) * cols;
-    for (int i = tid; i < ncell * cols; i += DEC_TILE) {
-        const int r = i / cols, c = i - r * cols;
-        dst[i] = tile[r * p.pitch + c];
+    if (p.pitch == cols) {  // odd row length: the tile is one contiguous run in shared memory too -- a flat copy
+        for (int i = tid; i < ncell * cols; i += DEC_TILE) dst[i] = tile[i];
+    } else {
+        for (int i = tid; i < ncell * cols; i += DEC_TILE) {
+            const int r = i / cols, c = i - r * cols;
+            dst[i] = tile[r * p.pitch + c];
+        }
     }
 }
 
