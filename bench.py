@@ -921,7 +921,7 @@ def _ref_modules():
     """The reference's own modules from oracle/_ref (staged by build(), see oracle/ref_stage.py), or None."""
     from oracle import ref_stage
 
-    if not ref_stage.staged() or not ref_stage.install(ref_stage.STAGED_ROOT):
+    if not ref_stage.staged() or not ref_stage.install(ref_stage.STAGED_ZIP):
         return None
     from kod.core.anchors.info import AnchorBoxInfo
     from kod.core.bbox.iou import IoUCalculator, IoUType

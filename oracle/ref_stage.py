@@ -1,9 +1,10 @@
 """oracle/_ref: the reference's OWN python files of the hot path, staged for the `--impl reference` arm of bench.py.
 
 TEST / MEASUREMENT INFRASTRUCTURE, NOT PRODUCT CODE.  The reference (craston/object_detection_cib, package `kod`) is
-pure Python: there is nothing to compile, so "building" oracle/_ref is `stage()` -- the `kod` package is copied
-UNMODIFIED from /root/reference into oracle/_ref/kod.  oracle/_ref/ is git-ignored (no reference source enters the
-history) but not gpurun-ignored, so the GPU box -- which has no /root/reference -- can time the real
+pure Python: there is nothing to compile, so "building" oracle/_ref is `stage()` -- the python files of the `kod`
+package are packed UNMODIFIED from /root/reference into ONE build artefact, oracle/_ref/kod_reference.zip (imported
+through zipimport).  oracle/_ref/ is git-ignored (no reference source enters the history) but not gpurun-ignored, so
+the GPU box -- which has no /root/reference -- can time the real
 `Yolov5Loss` (kod/lightning/experiments/yv5_baseline/loss.py:46-248), `DefaultYolov5Experiment.get_detections`
 (exp.py:70-102) and `non_max_suppression` (kod/core/nms.py:9-75) on its host cores.
 
@@ -24,22 +25,34 @@ STAGED_ROOT = os.path.join(HERE, "_ref")
 REFERENCE_ROOT = os.environ.get("KOD_REFERENCE_ROOT", "/root/reference")
 
 
-def stage(src_root: str = REFERENCE_ROOT, dst_root: str = STAGED_ROOT) -> bool:
-    """Copy the python files of `<src_root>/kod` to `<dst_root>/kod`.  False when the reference is absent."""
+STAGED_ZIP = os.path.join(STAGED_ROOT, "kod_reference.zip")
+
+
+def stage(src_root: str = REFERENCE_ROOT, dst_zip: str = STAGED_ZIP) -> bool:
+    """Pack the python files of `<src_root>/kod` into `dst_zip` (paths `kod/...`).  False when the reference is absent."""
+    import zipfile
+
     src = os.path.join(src_root, "kod")
     if not os.path.isdir(src):
         return False
-    dst = os.path.join(dst_root, "kod")
-    if os.path.isdir(dst):
-        shutil.rmtree(dst)
-    shutil.copytree(src, dst, ignore=lambda d, names: [n for n in names
-                                                        if not (n.endswith(".py") or os.path.isdir(os.path.join(d, n)))
-                                                        or n == "__pycache__"])
+    os.makedirs(os.path.dirname(dst_zip), exist_ok=True)
+    stale = os.path.join(os.path.dirname(dst_zip), "kod")
+    if os.path.isdir(stale):  # loose files of an earlier staging
+        shutil.rmtree(stale)
+    tmp = dst_zip + ".tmp"
+    with zipfile.ZipFile(tmp, "w", zipfile.ZIP_DEFLATED) as z:
+        for d, dirs, names in os.walk(src):
+            dirs[:] = sorted(x for x in dirs if x != "__pycache__")
+            for n in sorted(names):
+                if n.endswith(".py"):
+                    full = os.path.join(d, n)
+                    z.write(full, os.path.relpath(full, src_root))
+    os.replace(tmp, dst_zip)
     return True
 
 
 def staged() -> bool:
-    return os.path.isfile(os.path.join(STAGED_ROOT, "kod", "core", "nms.py"))
+    return os.path.isfile(STAGED_ZIP)
 
 
 def _stub(name: str, **attrs):
@@ -50,8 +63,9 @@ def _stub(name: str, **attrs):
 
 
 def install(root: str) -> bool:
-    """Make `import kod...` resolve to `<root>/kod`.  Returns False when that tree is absent."""
-    if not os.path.isdir(os.path.join(root, "kod")):
+    """Make `import kod...` resolve to `<root>/kod` (a directory tree) or to the staged zip (`root` = its path).  Returns
+    False when neither exists."""
+    if not (os.path.isdir(os.path.join(root, "kod")) or (root.endswith(".zip") and os.path.isfile(root))):
         return False
     if "kod" in sys.modules:
         return True
