@@ -1,20 +1,27 @@
-// kodb_head_forward — the Detect head of the reference (kod/nn/heads/yolov5.py:12-178): per pyramid level three 1x1
-// convolutions (box: A*4, objectness: A, class: A*C output channels, with bias) of the same (B, K, H, W) feature map,
-// each followed by Rearrange("b (a p) h w -> b a h w p") -- i.e. three planar [B][A*P][H][W] tensors.
+// kodb_head_forward / kodb_head_detections — the Detect head of the reference (kod/nn/heads/yolov5.py:12-178): per pyramid
+// level three 1x1 convolutions (box: A*4, objectness: A, class: A*C output channels, with bias) of the same (B, K, H, W)
+// feature map, each followed by Rearrange("b (a p) h w -> b a h w p") -- i.e. three planar [B][A*P][H][W] tensors
+//  -- and, on the eval side, get_detections (exp.py:70-102) of those outputs.
 //
 // Here: ONE persistent tcgen05 kernel for all three levels.  Per level the three convolutions are one GEMM
 //     D[cell][n] = sum_k X[b][k][cell] * W[n][k]          cell = 0..H*W-1 (M), n = 0..A*(5+C)-1 (N), k = 0..K-1
 // with the feature map read ONCE (the reference reads it three times) straight from its NCHW layout:
 //   * A operand = X tile, 128 cells x 32 channels, "MN-major" (cells contiguous): TMA boxes of 32 cells x 32 channels with
-//     the 128-byte swizzle are exactly the canonical UMMA MN-major SW128 atoms (8 channel rows x 128 B), no transposition;
-//   * B operand = the concatenated weights [n][k] (K-major), a 32-channel slab per stage, rows beyond A*(5+C) zero-filled
-//     by the TMA bounds check;
+//     the 128-byte swizzle / 32-byte atom -- the only legal shared-memory layout of an MN-major tf32 operand (UMMA layout
+//     type SWIZZLE_128B_BASE32B: atoms of 4 channel rows x 128 B) -- no transposition anywhere;
+//   * B operand = the concatenated weights [n][k] (K-major, 128-byte swizzle), a 32-channel slab per stage, rows beyond
+//     A*(5+C) zero-filled by the TMA bounds check;
 //   * tf32 MMA (fp32 operands, fp32 accumulation -- the precision class of torch's default conv policy
 //     torch.backends.cudnn.allow_tf32 = True), accumulators in TMEM: 128 lanes (cells) x N columns, double buffered;
-//   * warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread) + TMEM owner, warps 2..5 =
-//     epilogue (tcgen05.ld 32x32b: thread = cell, registers = channels; + bias; stores are 128-byte coalesced along the
-//     cells of ONE output plane, which is precisely the planar layout the detection tail wants).
+//   * warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread) + TMEM owner, warps 2..9 =
+//     epilogue, two per TMEM lane quadrant (tcgen05.ld 32x32b: thread = cell, registers = channels):
+//       planar  (<false>): + bias; one 16-byte shared-memory table read gives a channel's plane pointer; 32 lanes store 128
+//                contiguous bytes of ONE output plane -- precisely the planar layout the detection tail wants;
+//       decode  (<true>):  + bias, sigmoid / grid / anchor decode, rows of (x1, y1, x2, y2, obj, cls...) staged per warp and
+//                written as contiguous runs of the (B, AC, 5+C) detection tensor; the logits never reach memory;
+//   * scheduling units of equal load (16 k-blocks), heavy levels first, static round-robin over two CTAs per SM.
 // HBM-bound by construction (AI ~ 17 flop/B at K=128, N=45): 4*K bytes in + 4*N bytes out per cell.
+// Levels the TMA / tcgen05 path cannot take (H*W % 4, in_channels % 32, > 256 output channels) run on head_generic_kernel.
 #include <stdlib.h>
 
 #include <mutex>
