@@ -360,8 +360,8 @@ __global__ void __launch_bounds__(CAND_THREADS) cand_kernel(const __grid_constan
 // 1b. warp-autonomous candidate kernel for the planar float4 case (the shipped fused path)
 // ---------------------------------------------------------------------------------------------------------
 // One WARP owns a tile of up to 128 contiguous cells of one (level, anchor) plane: lane l holds cells 4l..4l+3.
-// Every global load of the tile (the obj float4 and the NQ class float4s of the lane) is issued before the first
-// use, so one DRAM round trip covers the tile; there is no block-level barrier on the data path.  The per-pair
+// The tile is brought into a warp-private shared stash in one go (TMA bulk tensor copies, or cp.async for odd strides),
+// so one DRAM round trip covers the tile; there is no block-level barrier on the data path.  The per-pair
 // decision is one subtraction whose sign bit is funnel-shifted into a mask:  sigmoid(q)*o > thr  <=>  q > tau(o)
 // with tau = logit(thr/o) in exact arithmetic; pairs with |q - tau| <= TAU_WINDOW (a few per thousand) are
 // re-decided with the decode kernel's exact fp32 product, so the candidate set is the one kodb_decode + kodb_nms
@@ -397,8 +397,9 @@ struct CandWarpSmem {  // one per warp: the data path of the kernel has no block
 
 // Candidate kernel of the fused path.  One WARP owns a tile of up to 128 contiguous cells of one (level, anchor)
 // plane: lane l holds cells 4l..4l+3.  No block-level barrier, no waiting on other CTAs.
-//  * Every global load of the tile (the obj float4 and the NQ class float4s of the lane, evict-first) is issued
-//    before the first use: one DRAM round trip per tile.
+//  * The tile (128 cells x 1 objectness plane + 128 cells x NQ class planes) arrives in the warp's shared stash by two
+//    TMA bulk tensor copies on a per-warp mbarrier (class planes with the L2 evict-first hint); head tensors that are
+//    not flat planar arrays use per-lane cp.async 16-byte copies instead.  Either way: one DRAM round trip per tile.
 //  * The per-pair decision is one subtraction whose sign bit is funnel-shifted into a mask:
 //    sigmoid(q)*o > thr  <=>  q > tau(o) = logit(thr/o) in exact arithmetic; pairs with |q - tau| <= TAU_WINDOW (a
 //    few per thousand) are re-decided with the decode kernel's exact fp32 product, so the candidate set is the one
