@@ -466,9 +466,10 @@ __global__ void __launch_bounds__(CW_WARPS * 32, 6) cand_floor_kernel(const __gr
     planar_tile(p.g, t, L, a, c0, ncell);
     const kodb_head_level& hd = p.g.head[L];
     const int row0 = p.g.row_base[L] + a * (p.g.lv[L].H * p.g.lv[L].W) + c0;
-    const float* obj_base = hd.obj + (int64_t)b * hd.obj_sb + (int64_t)a * hd.obj_sa + c0;
-    const float* cls_base = hd.cls + (int64_t)b * hd.cls_sb + (int64_t)a * hd.cls_sa + c0;
-    const int64_t cls_step = hd.cls_sp;
+    // (tile base addresses: needed by the cp.async path only -- computed where they are used, so that the TMA path,
+    // which addresses the tile by coordinates, does not pay for the 64-bit arithmetic)
+    auto obj_base_of = [&]() { return hd.obj + (int64_t)b * hd.obj_sb + (int64_t)a * hd.obj_sa + c0; };
+    auto cls_base_of = [&]() { return hd.cls + (int64_t)b * hd.cls_sb + (int64_t)a * hd.cls_sa + c0; };
     const int cell0 = lane * 4;
     const bool in_range = cell0 < ncell;  // tiles are multiples of 4 cells
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -493,10 +494,11 @@ __global__ void __launch_bounds__(CW_WARPS * 32, 6) cand_floor_kernel(const __gr
     } else {
         // Asynchronous 16-byte copies global -> the warp's shared stash (LDGSTS): all of the tile's bytes are in flight
         // at once without holding registers.  The obj logits land in sm.o and are replaced by their sigmoid below.
-        if (in_range) cp_async16(&sm.o[cell0], obj_base + cell0);  // (normal policy: the loss reads the obj planes too)
+        const int64_t cls_step = hd.cls_sp;
+        if (in_range) cp_async16(&sm.o[cell0], obj_base_of() + cell0);  // (normal policy: the loss reads the obj planes too)
         else *reinterpret_cast<float4*>(&sm.o[cell0]) = zero4;
         const int nld = in_range ? min(C, CGROUP) : 0;
-        const float* cp = cls_base + cell0;
+        const float* cp = cls_base_of() + cell0;
         if (nld == NQ) {  // the usual case: every class slot of the group is real -- no per-copy predicate
 #pragma unroll
             for (int u = 0; u < NQ; ++u) cp_async16_s_ef(sq0 + u * (WT_CELLS * 4), cp + (int64_t)u * cls_step, l2pol);
@@ -581,7 +583,8 @@ __global__ void __launch_bounds__(CW_WARPS * 32, 6) cand_floor_kernel(const __gr
                 mbar_wait(tbar, tile_phase);
                 tile_phase ^= 1u;
             } else {
-                const float* cp = cls_base + (int64_t)j0 * cls_step + cell0;
+                const int64_t cls_step = hd.cls_sp;
+                const float* cp = cls_base_of() + (int64_t)j0 * cls_step + cell0;
                 const int nld = in_range ? jn : 0;
 #pragma unroll
                 for (int u = 0; u < NQ; ++u) {
