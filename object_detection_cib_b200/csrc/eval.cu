@@ -430,7 +430,9 @@ __global__ void __launch_bounds__(CW_WARPS * 32, 6) cand_floor_kernel(const __gr
     extern __shared__ __align__(128) unsigned char cw_smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     // (128-byte alignment of the stashes: destination of the TMA tile loads)
-    unsigned char* cw_smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(cw_smem_raw) + 127) & ~(uintptr_t)127);
+    // (offset arithmetic on the shared array itself, not an integer round trip: the compiler keeps the shared address
+    // space and emits LDS / STS instead of generic loads and stores)
+    unsigned char* cw_smem = cw_smem_raw + ((128u - ((unsigned)__cvta_generic_to_shared(cw_smem_raw) & 127u)) & 127u);
     CandWarpSmem<NQ>& sm = reinterpret_cast<CandWarpSmem<NQ>*>(cw_smem)[wid];
     __shared__ __align__(8) uint64_t s_tile_bar[CW_WARPS];  // one mbarrier per warp: arrival of the warp's tile (TMA path)
     // work order: CTA b < B is image b's sample CTA (one sample tile per warp, tiles 0, S, 2S, ...; it runs first and

@@ -144,7 +144,8 @@ template <bool DECODE>
 __global__ void __launch_bounds__(HD_THREADS, 2) head_forward_kernel(const __grid_constant__ HeadParams p) {
     extern __shared__ __align__(1024) uint8_t hd_smem_raw[];
     // 1024-byte alignment of every operand stage (128B swizzle atoms are 1 KB)
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(hd_smem_raw) + 1023) & ~(uintptr_t)1023);
+    // (offset arithmetic on the shared array, not an integer round trip: keeps the shared address space -> LDS / STS)
+    uint8_t* smem = hd_smem_raw + ((1024u - (smem_u32(hd_smem_raw) & 1023u)) & 1023u);
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + HD_STAGES * HD_A_STAGE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + HD_STAGES * p.b_stage_bytes);
