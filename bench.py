@@ -2,7 +2,7 @@
 """Benchmark of the YOLOv5s detection tail (BASELINE.json metric: head+loss+NMS images/s).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's own CPU path (its files from oracle/_ref)
 
 One "step" = one pass of the hot path over one batch of `--batch` images per GPU (default: config[1] of
 BASELINE.json, 64 images/GPU at 640x640, 10 classes, class-weighted loss):
@@ -11,11 +11,14 @@ BASELINE.json, 64 images/GPU at 640x640, 10 classes, class-weighted loss):
   eval tail  : sigmoid/grid/anchor decode + conf 0.001 filter + class-offset NMS (IoU 0.6, 300/img)
                + per-class COCO matching (kodb_eval_tail, two kernels)
 `value` is device-resident throughput: the K timed steps are ONE CUDA-graph launch (device-bound: the host is out
-of the picture), consecutive steps pipelined over one graph branch per input set; CUDA events, max over ranks, with
-the per-rank spread and the strictly-in-order one-stream step reported beside it.  `e2e` goes through the public
+of the picture); per input set an eval chain (candidates -> select/NMS) and an independent train chain, consecutive steps
+pipelined over the input sets; CUDA events, max over ranks, with the per-rank spread and the strictly-in-order one-stream
+step reported beside it.  `e2e` goes through the public
 Python drop-ins with host buffers (H2D of the head maps and targets, D2H of losses/detections/records inside the
 timed region).  `extra_configs` holds the other BASELINE configurations (eval B=128, exactly 10 targets/image,
-1280x1280 with 80 classes), each with its own roofline block.  Under torchrun rank 0 also recomputes the AP over the
+1280x1280 with 80 classes), each with its own roofline block, and the Detect head (one tcgen05 launch,
+planar and decode epilogue) against the reference's nine cuDNN convolutions.  `roofline.hbm_probe`: what plain fill / read /
+copy kernels reach on this box, alone and concurrently.  Under torchrun rank 0 also recomputes the AP over the
 union of all ranks' detections in one process and checks the NCCL-gathered global AP against it (`map_check`).
 Prints ONE JSON line on rank 0.
 """
