@@ -193,7 +193,9 @@ int kodb_head_forward(const kodb_head_conv_level* levels_h /* [num_levels], 1..3
 /* kodb_head_detections: the eval side of the same GEMM -- get_detections(Yolov5Head.forward(x)) (exp.py:70-102 on top of
  * yolov5.py:170-178) in ONE launch: the epilogue decodes the accumulators (sigmoid / grid / anchor, layers.py:55-89) and
  * writes the (B, AC, 5+C) detection rows (rows ll|ml|hl, r = (a*H+y)*W+x; columns x1,y1,x2,y2,sigmoid(obj),sigmoid(cls));
- * the planar logits are never written (out_* of the levels are ignored).  level_cfg_h[l] gives stride / anchors / grid of
+ * the planar logits are never written (out_* of the levels are ignored).  Precision: tf32 logits like kodb_head_forward; the
+ * epilogue's sigmoid is ex2.approx / rcp.approx (~1e-6 relative, far below the tf32 error), so probabilities agree with
+ * kodb_decode(kodb_head_forward(x)) to ~3e-6 relative and box corners to ~1e-3 px.  level_cfg_h[l] gives stride / anchors / grid of
  * levels_h[l].  Tensor-core path only: KODB_ERR_UNSUPPORTED for a level outside it (see kodb_head_forward; callers then
  * run kodb_head_forward + kodb_decode). */
 int kodb_head_detections(const kodb_head_conv_level* levels_h /* [num_levels] */, const kodb_level_cfg* level_cfg_h,
