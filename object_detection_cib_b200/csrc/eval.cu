@@ -733,11 +733,17 @@ __global__ void __launch_bounds__(CW_WARPS * 32, 6) cand_floor_kernel(const __gr
         } else {
             // the few pairs that reach the floor: ONE loop over the lane's four cell masks (most lanes have none)
             int slot = warp_excl_scan_i(hot, lane);
-            unsigned long long hb = (unsigned long long)(hm[0] | (hm[1] << 16)) | ((unsigned long long)(hm[2] | (hm[3] << 16)) << 32);
-            while (hb) {
-                const int bi = __ffsll((long long)hb) - 1;
-                hb &= hb - 1;
+            // (two 32-bit halves: 32-bit find-first-set / clear-lowest are one instruction each, the 64-bit forms four)
+            unsigned h01 = hm[0] | (hm[1] << 16), h23 = hm[2] | (hm[3] << 16);
+            while (h01) {
+                const int bi = __ffs((int)h01) - 1;
+                h01 &= h01 - 1;
                 sm.list[slot++] = (unsigned short)(((cell0 + (bi >> 4)) << 4) | (bi & 15));
+            }
+            while (h23) {
+                const int bi = __ffs((int)h23) - 1;
+                h23 &= h23 - 1;
+                sm.list[slot++] = (unsigned short)(((cell0 + 2 + (bi >> 4)) << 4) | (bi & 15));
             }
         }
         __syncwarp();  // list, q stash and o are visible to the whole warp
